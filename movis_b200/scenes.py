@@ -1,0 +1,217 @@
+"""Synthetic scenes for BASELINE.json's configs (S1..S5).
+
+Every builder takes the API module as its first argument and only uses the public movis API
+(``mv.layer.Composition``, ``mv.layer.Image``, ``add_layer``, ``enable_motion`` ...), so the SAME
+builder constructs the scene on the reference package (for golden vectors, in the build
+container), on this package (the product) and for the oracle's scene walker.  ``div`` shrinks every
+pixel dimension by an integer factor so parity tests can run the same scene at a size a CPU
+finishes in seconds; ``div=1`` is the configuration the benchmark is quoted on.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+BLEND_MODE_NAMES = [
+    "normal", "multiply", "screen", "overlay", "darken", "lighten", "color_dodge", "color_burn",
+    "linear_dodge", "linear_burn", "hard_light", "soft_light", "vivid_light", "linear_light",
+    "pin_light", "difference", "exclusion", "subtract",
+]
+
+
+def synthetic_rgba(seed: int, h: int, w: int, alpha: str = "random", rim: int = 0) -> np.ndarray:
+    """Uniform-random RGBA; ``alpha`` in {'random', 'opaque'}; ``rim`` px of full transparency."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    if alpha == "opaque":
+        img[..., 3] = 255
+    if rim > 0:
+        r = min(rim, h // 2, w // 2)
+        if r > 0:
+            img[:r, :, 3] = 0
+            img[-r:, :, 3] = 0
+            img[:, :r, 3] = 0
+            img[:, -r:, 3] = 0
+    return img
+
+
+def _ramp(attr: Any, t0: float, t1: float, v0: Any, v1: Any, easing: str = "linear") -> None:
+    attr.enable_motion().extend(keyframes=[t0, t1], values=[v0, v1], easings=[easing])
+
+
+def _wrapped_ramp(attr: Any, duration: float, lo: float, hi: float, phase: float) -> None:
+    """lo -> hi ramp over ``duration`` shifted by ``phase`` in [0, 1) and wrapped around."""
+    m = attr.enable_motion()
+    if phase <= 0.0:
+        m.extend([0.0, duration], [lo, hi])
+        return
+    v_start = lo + (hi - lo) * phase
+    t_wrap = duration * (1.0 - phase)
+    m.extend([0.0, t_wrap, t_wrap + 1e-6, duration], [v_start, hi, lo, v_start])
+
+
+# ---------------------------------------------------------------------------------------------
+# S1 (config 0): 1080p, colour background + 8 rotating/scaling NORMAL layers
+# ---------------------------------------------------------------------------------------------
+
+def build_s1(mv: Any, div: int = 1, duration: float = 5.0):
+    W, H, S = 1920 // div, 1080 // div, 512 // div
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    comp.add_layer(mv.layer.Image.from_color((W, H), (32, 64, 96)), name="bg")
+    for i in range(8):
+        img = synthetic_rgba(1000 + i, S, S, alpha="opaque" if i % 2 == 0 else "random")
+        item = comp.add_layer(mv.layer.Image(img), name=f"l{i}")
+        _ramp(item.position, 0.0, duration, ((520 + 110 * i) / div, 540 / div),
+              ((1400 - 110 * i) / div, 540 / div), "ease_in_out3")
+        _ramp(item.scale, 0.0, duration, (1.0, 1.0), (1.4, 1.4), "linear")
+        _ramp(item.rotation, 0.0, duration, 0.0, 360.0, "ease_out5")
+    return comp
+
+
+def s1_bytes_per_frame(div: int = 1) -> int:
+    W, H, S = 1920 // div, 1080 // div, 512 // div
+    return 4 * W * H + 4 * W * H + 8 * 4 * S * S
+
+
+# ---------------------------------------------------------------------------------------------
+# S2 (config 1, the headline): 4K, 16 x 1080p layers cycling every blend mode, animated opacity
+# ---------------------------------------------------------------------------------------------
+
+def s2_sources(div: int = 1) -> list[np.ndarray]:
+    lw, lh = 1920 // div, 1080 // div
+    out = []
+    for i in range(16):
+        out.append(synthetic_rgba(2000 + i, lh, lw, alpha="opaque" if i % 4 == 0 else "random",
+                                  rim=(64 // div) if i % 5 == 0 else 0))
+    return out
+
+
+def build_s2(mv: Any, div: int = 1, variant: int = 0, duration: float = 5.0, sources=None):
+    W, H = 3840 // div, 2160 // div
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    if sources is None:
+        sources = s2_sources(div)
+    for i in range(16):
+        mode = BLEND_MODE_NAMES[(i + variant) % 18]
+        item = comp.add_layer(
+            mv.layer.Image(sources[i]), name=f"l{i}",
+            position=((1400 + 70 * i) / div, (1040 + 5 * i) / div), blending_mode=mode)
+        _ramp(item.scale, 0.0, duration, (1.0, 1.0), (1.2, 1.2))
+        _ramp(item.rotation, 0.0, duration, float(2 * i - 15), float(15 - 2 * i))
+        _wrapped_ramp(item.opacity, duration, 0.2, 1.0, i / 16.0)
+    return comp
+
+
+def s2_bytes_per_frame(div: int = 1) -> int:
+    return 4 * (3840 // div) * (2160 // div) + 16 * 4 * (1920 // div) * (1080 // div)
+
+
+# ---------------------------------------------------------------------------------------------
+# S2d: dense variant, 16 full-frame layers, translations only
+# ---------------------------------------------------------------------------------------------
+
+def build_s2d(mv: Any, div: int = 1, variant: int = 0, duration: float = 5.0):
+    W, H = 3840 // div, 2160 // div
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    for i in range(16):
+        img = synthetic_rgba(2500 + i, H, W, alpha="opaque" if i % 4 == 0 else "random")
+        mode = BLEND_MODE_NAMES[(i + variant) % 18]
+        item = comp.add_layer(mv.layer.Image(img), name=f"d{i}", blending_mode=mode,
+                              opacity=0.3 + 0.04 * i)
+        if i % 2 == 1:  # fractional drift for the odd layers, integer placement for the even ones
+            _ramp(item.position, 0.0, duration, (W / 2, H / 2), (W / 2 + 0.75, H / 2 - 0.5))
+    return comp
+
+
+def s2d_bytes_per_frame(div: int = 1) -> int:
+    return 17 * 4 * (3840 // div) * (2160 // div)
+
+
+# ---------------------------------------------------------------------------------------------
+# S3 (config 2): nested 1080p comp with GaussianBlur / DropShadow / Glow inside a 4K parent
+# ---------------------------------------------------------------------------------------------
+
+def build_s3(mv: Any, div: int = 1, duration: float = 5.0):
+    iw, ih, S = 1920 // div, 1080 // div, 400 // div
+    inner = mv.layer.Composition(size=(iw, ih), duration=duration)
+    inner.add_layer(mv.layer.Image.from_color((iw, ih), (200, 180, 40)), name="ibg", opacity=0.5)
+    radius = 10.0 / div
+    effects = [
+        mv.effect.GaussianBlur(radius=radius),
+        mv.effect.DropShadow(radius=radius, offset=20.0 / div, angle=45.0, opacity=0.5),
+        mv.effect.Glow(radius=radius, strength=1.0),
+    ]
+    for i, x in enumerate((460, 960, 1460)):
+        img = synthetic_rgba(3000 + i, S, S, alpha="random", rim=S // 8)
+        item = inner.add_layer(mv.layer.Image(img), name=f"e{i}", position=(x / div, 540 / div))
+        _ramp(item.rotation, 0.0, duration, 0.0, 90.0)
+        item.add_effect(effects[i])
+    W, H = 3840 // div, 2160 // div
+    outer = mv.layer.Composition(size=(W, H), duration=duration)
+    outer.add_layer(mv.layer.Image.from_color((W, H), (16, 24, 32)), name="bg")
+    item = outer.add_layer(inner, name="nested")
+    _ramp(item.scale, 0.0, duration, (1.5, 1.5), (1.8, 1.8))
+    _ramp(item.rotation, 0.0, duration, 0.0, 30.0)
+    return outer
+
+
+# ---------------------------------------------------------------------------------------------
+# S4 (config 3): chroma-keyed frame sequence over an animated background, draft levels
+# ---------------------------------------------------------------------------------------------
+
+def s4_sequence(div: int = 1, n: int = 8) -> list[np.ndarray]:
+    W, H = 3840 // div, 2160 // div
+    frames = []
+    for j in range(n):
+        f = synthetic_rgba(4100 + j, H, W, alpha="opaque")
+        f[: H // 2, :, 0] = 0
+        f[: H // 2, :, 1] = 255
+        f[: H // 2, :, 2] = 0
+        frames.append(f)
+    return frames
+
+
+def build_s4(mv: Any, chroma_key_cls: Any, div: int = 1, duration: float = 5.0, n_seq: int = 8):
+    W, H = 3840 // div, 2160 // div
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    bg = synthetic_rgba(4000, 2400 // div, 4200 // div, alpha="opaque")
+    item = comp.add_layer(mv.layer.Image(bg), name="bg")
+    _ramp(item.position, 0.0, duration, (1900 / div, 1080 / div), (1940 / div, 1080 / div))
+    seq = mv.layer.ImageSequence.from_files(s4_sequence(div, n_seq), each_duration=1.0 / 30.0)
+    fg = comp.add_layer(seq, name="fg", end_time=duration)
+    fg.add_effect(chroma_key_cls())
+    return comp
+
+
+# ---------------------------------------------------------------------------------------------
+# generic mixed scene for parity fuzzing (overhanging layers, anisotropic scale, every mode)
+# ---------------------------------------------------------------------------------------------
+
+def build_fuzz(mv: Any, seed: int, size=(160, 90), n_layers: int = 18, duration: float = 2.0):
+    rng = np.random.default_rng(seed)
+    W, H = size
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    origins = ["center", "top_left", "bottom_right", "center_left", "top_center"]
+    for i in range(n_layers):
+        h, w = (int(v) for v in rng.integers(4, max(H, 8), 2))
+        alpha = ["random", "opaque"][int(rng.integers(0, 2))]
+        img = synthetic_rgba(seed * 100 + i, h, w, alpha=alpha, rim=int(rng.integers(0, 3)))
+        kw = dict(
+            position=(float(rng.uniform(-0.2 * W, 1.2 * W)), float(rng.uniform(-0.2 * H, 1.2 * H))),
+            scale=(float(rng.uniform(0.3, 2.5)), float(rng.uniform(0.3, 2.5))),
+            rotation=float(rng.uniform(-180, 180)),
+            opacity=[1.0, float(rng.uniform(0, 1))][int(rng.integers(0, 2))],
+            blending_mode=BLEND_MODE_NAMES[(i + seed) % 18],
+            origin_point=origins[int(rng.integers(0, len(origins)))],
+            anchor_point=(float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5))),
+        )
+        if i % 6 == 5:  # integer placement, no resampling
+            kw.update(position=(float(rng.integers(0, W)), float(rng.integers(0, H))), scale=(1.0, 1.0),
+                      rotation=0.0, origin_point="top_left", anchor_point=(0.0, 0.0))
+        item = comp.add_layer(mv.layer.Image(img), name=f"f{i}", **kw)
+        if i % 3 == 0:
+            _ramp(item.rotation, 0.0, duration, kw["rotation"], kw["rotation"] + 40.0, "ease_in_out2")
+        if i % 4 == 1:
+            _ramp(item.opacity, 0.0, duration, 0.1, 0.9, "ease_out3")
+    return comp
