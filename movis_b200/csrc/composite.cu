@@ -1,0 +1,368 @@
+// composite.cu -- fused multi-layer warp + blend kernel and the stand-alone warp / alpha_composite
+// operators (sm_100a).  C ABI in include/movis_b200.h.
+//
+// Replaces, per frame, the reference's per-layer pair cv2.warpAffine -> alpha_composite
+// (movis/layer/composition.py:811-819) and the frame walk around it (composition.py:363-368).
+//
+// Data layout: frame and sources are uint8 RGBA HWC in HBM.  One CTA owns a 32x32 output tile:
+//   prologue  - cull layers whose bbox misses the tile; for the survivors build, in shared memory,
+//               cv::warpAffine's integer tables restricted to the tile (adelta/bdelta for the 32
+//               columns, X0/Y0 for the 32 rows; fp64 without FMA contraction) and a 256-entry
+//               alpha LUT that applies the layer opacity exactly like the reference path does;
+//   main loop - each thread owns one column and 8 rows; for each of its pixels it walks the
+//               surviving layers in paint order with the pixel in a register (re-quantised to
+//               4xu8 after every layer, as the reference does), gathering the 4 bilinear taps
+//               through L1 and blending with exact integer arithmetic;
+//   epilogue  - one coalesced 128-byte store per warp row.  The frame is written exactly once.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/movis_b200.h"
+#include "host_util.h"
+#include "pixel_math.cuh"
+
+namespace mvb {
+
+constexpr int kTileW = 32;
+constexpr int kTileH = 32;
+constexpr int kWarps = 4;
+constexpr int kMaxLayers = 32; // per launch; 32 * 104 B of descriptors stay under the 4 KB param limit
+
+struct DevLayer {
+    const uint8_t* src;
+    int32_t src_w, src_h;
+    int32_t src_stride;
+    int32_t mode;       // MVB_BLEND_*
+    double m[6];        // inverse map: bbox px -> layer px (OpenCV's own inversion, done on host)
+    int32_t bx, by, bw, bh;
+    double opacity;
+    int32_t pil;        // 1: PIL over
+    int32_t pil_a;      // int(round(opacity * 255)) for the PIL path (imgproc.py:207)
+};
+static_assert(sizeof(DevLayer) == 104, "descriptor layout");
+
+struct StackParams {
+    uint8_t* frame;
+    int32_t W, H;
+    int32_t stride;
+    uint32_t bg;
+    int32_t n_layers;
+    int32_t keep_frame;
+    DevLayer layers[kMaxLayers];
+};
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_composite_stack(const __grid_constant__ StackParams P)
+{
+    __shared__ int2 s_col[kMaxLayers][kTileW];     // (adelta, bdelta) per tile column
+    __shared__ int2 s_row[kMaxLayers][kTileH];     // (X0, Y0) per tile row
+    __shared__ uint8_t s_lut[kMaxLayers][256];     // opacity-scaled alpha
+    __shared__ int s_active[kMaxLayers];
+    __shared__ int s_nactive;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
+
+    // ---- prologue: cull + tables -----------------------------------------------------------
+    if (warp == 0) {
+        bool hit = false;
+        if (lane < P.n_layers) {
+            const DevLayer& L = P.layers[lane];
+            hit = L.bw > 0 && L.bh > 0 && tx0 < L.bx + L.bw && tx0 + kTileW > L.bx &&
+                  ty0 < L.by + L.bh && ty0 + kTileH > L.by;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hit) s_active[__popc(m & ((1u << lane) - 1u))] = lane;
+        if (lane == 0) s_nactive = __popc(m);
+    }
+    __syncthreads();
+    const int n_active = s_nactive;
+
+    for (int i = tid; i < n_active * (kTileW + kTileH); i += kWarps * 32) {
+        const int slot = i / (kTileW + kTileH), j = i % (kTileW + kTileH);
+        const DevLayer& L = P.layers[s_active[slot]];
+        if (j < kTileW) {
+            const int u = tx0 + j - L.bx;
+            s_col[slot][j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
+        } else {
+            const int v = ty0 + (j - kTileW) - L.by;
+            s_row[slot][j - kTileW] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
+        }
+    }
+    for (int i = tid; i < n_active * 256; i += kWarps * 32) {
+        const int slot = i >> 8, a = i & 255;
+        const DevLayer& L = P.layers[s_active[slot]];
+        uint32_t v = (uint32_t)a;
+        if (L.opacity < 1.0) {
+            v = L.pil ? (uint32_t)(a * L.pil_a) / 255u                      // imgproc.py:206-208
+                      : __double2uint_rz(__dmul_rn((double)a, L.opacity));  // imgproc.py:159
+        }
+        s_lut[slot][a] = (uint8_t)v;
+    }
+    __syncthreads();
+
+    // ---- main loop -------------------------------------------------------------------------
+    const int x = tx0 + lane;
+    if (x >= P.W) return;
+#pragma unroll 1
+    for (int rr = 0; rr < kTileH / kWarps; ++rr) {
+        const int row = rr * kWarps + warp;
+        const int y = ty0 + row;
+        if (y >= P.H) break;
+        uint32_t* out = reinterpret_cast<uint32_t*>(P.frame + (int64_t)y * P.stride) + x;
+        uint32_t px = P.keep_frame ? *out : P.bg;
+#pragma unroll 1
+        for (int slot = 0; slot < n_active; ++slot) {
+            const DevLayer& L = P.layers[s_active[slot]];
+            const int u = x - L.bx, v = y - L.by;
+            if ((unsigned)v >= (unsigned)L.bh || (unsigned)u >= (unsigned)L.bw) continue;
+            const int2 c = s_col[slot][lane];
+            const int2 r = s_row[slot][row];
+            const int X = (r.x + c.x) >> 5, Y = (r.y + c.y) >> 5;
+            Rgba s;
+            uint32_t fa = 0;
+            if (sample_q5(L.src, L.src_w, L.src_h, L.src_stride, X, Y, s)) fa = s_lut[slot][s.a];
+            else s = Rgba{0, 0, 0, 0};
+            if (L.pil) {
+                px = over_pil(px, s, fa);
+            } else if (fa == 0) {
+                // numpy path with a transparent sample: no-op unless bg alpha is 0, where the
+                // reference zeroes rgb (imgproc.py:164 with out_a == 0)
+                if ((px >> 24) == 0) px = 0;
+            } else {
+                px = over_numpy_dyn(L.mode, px, s, fa, false);
+            }
+        }
+        *out = px;
+    }
+}
+
+// cv2.warpAffine stand-alone: one thread per destination pixel.
+__global__ void __launch_bounds__(256)
+k_warp_affine(const uint8_t* __restrict__ src, int sw, int sh, int sstride, uint8_t* __restrict__ dst,
+              int dw, int dh, int dstride, const double m0, const double m1, const double m2,
+              const double m3, const double m4, const double m5)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const double m[6] = {m0, m1, m2, m3, m4, m5};
+    const int X = (warp_x0(m, y) + warp_adelta(m, x)) >> 5;
+    const int Y = (warp_y0(m, y) + warp_bdelta(m, x)) >> 5;
+    Rgba s;
+    uint32_t o = 0;
+    if (sample_q5(src, sw, sh, sstride, X, Y, s)) o = pack(s.r, s.g, s.b, s.a);
+    reinterpret_cast<uint32_t*>(dst + (int64_t)y * dstride)[x] = o;
+}
+
+struct OverParams {
+    uint8_t* bg;
+    int32_t bw, bh, bstride;
+    const uint8_t* fg;
+    int32_t fstride;
+    int32_t x1, y1, x2, y2, w, h; // intersection: bg origin, fg origin, size (imgproc.py:184-187)
+    int32_t mode, matte, pil, pil_a;
+    double opacity;
+};
+
+// movis.imgproc.alpha_composite: one thread per bg pixel of the region (whole bg for LUMINANCE).
+__global__ void __launch_bounds__(256)
+k_alpha_composite(const __grid_constant__ OverParams P)
+{
+    __shared__ uint8_t s_lut[256];
+    {
+        const int a = threadIdx.x;
+        uint32_t v = (uint32_t)a;
+        if (P.opacity < 1.0)
+            v = P.pil ? (uint32_t)(a * P.pil_a) / 255u : __double2uint_rz(__dmul_rn((double)a, P.opacity));
+        s_lut[a] = (uint8_t)v;
+    }
+    __syncthreads();
+    const bool lum = (P.matte == MVB_MATTE_LUMINANCE) && !P.pil;
+    const int gx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int gy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    // LUMINANCE touches the whole background (imgproc.py:152); other modes only the region.
+    const int x = lum ? gx : P.x1 + gx;
+    const int y = lum ? gy : P.y1 + gy;
+    if (lum ? (x >= P.bw || y >= P.bh) : (gx >= P.w || gy >= P.h)) return;
+    uint32_t* dp = reinterpret_cast<uint32_t*>(P.bg + (int64_t)y * P.bstride) + x;
+    const bool inside = x >= P.x1 && x < P.x1 + P.w && y >= P.y1 && y < P.y1 + P.h;
+    if (!inside) { // only reachable for LUMINANCE
+        *dp &= 0x00FFFFFFu;
+        return;
+    }
+    const uint32_t spx = reinterpret_cast<const uint32_t*>(
+        P.fg + (int64_t)(y - P.y1 + P.y2) * P.fstride)[x - P.x1 + P.x2];
+    const Rgba s = unpack(spx);
+    const uint32_t fa = s_lut[s.a];
+    uint32_t d = *dp;
+    if (lum) { // imgproc.py:147-154
+        const uint32_t mask = rgb_to_gray(unpack(d));
+        d = (spx & 0x00FFFFFFu) | (((mask * fa) / 255u) << 24);
+    } else if (P.pil) {
+        d = over_pil(d, s, fa);
+    } else {
+        d = over_numpy_dyn(P.mode, d, s, fa, P.matte == MVB_MATTE_ALPHA);
+    }
+    *dp = d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+static int fill_dev_layer(const mvb_layer& in, DevLayer& out)
+{
+    if (in.bbox_w <= 0 || in.bbox_h <= 0) {
+        std::memset(&out, 0, sizeof(out));
+        return 0; // skipped by the kernel's cull (bw <= 0)
+    }
+    if (!in.src || in.src_w <= 0 || in.src_h <= 0 || in.src_w >= 32768 || in.src_h >= 32768)
+        return set_error(MVB_ERR_INVALID_ARG, "layer source must be non-null and 1..32767 px per side");
+    if (in.src_stride < (int64_t)in.src_w * 4 || (in.src_stride & 3) || in.src_stride > 0x7FFFFFFF ||
+        (reinterpret_cast<uintptr_t>(in.src) & 3))
+        return set_error(MVB_ERR_INVALID_ARG, "layer source stride/pointer must be 4-byte aligned and >= 4*width");
+    if (in.blend_mode < 0 || in.blend_mode >= MVB_BLEND_COUNT)
+        return set_error(MVB_ERR_INVALID_ARG, "unknown blend mode");
+    if (!(in.opacity >= 0.0 && in.opacity <= 1.0))
+        return set_error(MVB_ERR_INVALID_ARG, "opacity must be in [0, 1]");
+    out.src = static_cast<const uint8_t*>(in.src);
+    out.src_w = in.src_w;
+    out.src_h = in.src_h;
+    out.src_stride = (int32_t)in.src_stride;
+    out.mode = in.blend_mode;
+    invert_affine_cv(in.M, out.m);
+    out.bx = in.bbox_x;
+    out.by = in.bbox_y;
+    out.bw = in.bbox_w;
+    out.bh = in.bbox_h;
+    out.opacity = in.opacity;
+    out.pil = (in.flags & MVB_LAYER_PIL_OVER) ? 1 : 0;
+    out.pil_a = (int32_t)std::nearbyint(in.opacity * 255.0);
+    return 0;
+}
+
+static int check_image(const void* p, int w, int h, int64_t stride, const char* what)
+{
+    if (!p || w <= 0 || h <= 0 || stride < (int64_t)w * 4 || (stride & 3) || stride > 0x7FFFFFFF ||
+        (reinterpret_cast<uintptr_t>(p) & 3)) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "%s: need non-null 4-byte-aligned RGBA8 image with stride >= 4*width", what);
+        return set_error(MVB_ERR_INVALID_ARG, buf);
+    }
+    return 0;
+}
+
+static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t bg[4], int n_layers,
+                        const mvb_layer* layers, int flags, cudaStream_t stream)
+{
+    StackParams P;
+    P.frame = static_cast<uint8_t*>(frame);
+    P.W = W;
+    P.H = H;
+    P.stride = (int32_t)stride;
+    std::memcpy(&P.bg, bg, 4);
+    const dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH);
+    int done = 0;
+    bool first = true;
+    do {
+        const int n = n_layers - done < kMaxLayers ? n_layers - done : kMaxLayers;
+        for (int i = 0; i < n; i++) {
+            int rc = fill_dev_layer(layers[done + i], P.layers[i]);
+            if (rc) return rc;
+        }
+        P.n_layers = n;
+        P.keep_frame = (!first || (flags & MVB_STACK_KEEP_FRAME)) ? 1 : 0;
+        k_composite_stack<<<grid, kWarps * 32, 0, stream>>>(P);
+        done += n;
+        first = false;
+    } while (done < n_layers);
+    return check_launch("mvb_composite_stack");
+}
+
+} // namespace mvb
+
+using namespace mvb;
+
+extern "C" int mvb_max_layers_per_launch(void) { return kMaxLayers; }
+
+extern "C" int mvb_composite_stack(void* frame, int32_t W, int32_t H, int64_t stride, const uint8_t bg_color[4],
+                                   int32_t n_layers, const mvb_layer* layers, int32_t flags, mvb_stream_t stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_image(frame, W, H, stride, "frame")) return rc;
+    if (!bg_color || n_layers < 0 || (n_layers > 0 && !layers))
+        return set_error(MVB_ERR_INVALID_ARG, "bad bg_color / layers");
+    return launch_stack(frame, W, H, stride, bg_color, n_layers, layers, flags, (cudaStream_t)stream);
+}
+
+extern "C" int mvb_composite_frames(int32_t n_frames, void* const* frames, int32_t W, int32_t H, int64_t stride,
+                                    const uint8_t bg_color[4], const int32_t* layer_offsets,
+                                    const mvb_layer* layers, int32_t flags, mvb_stream_t stream)
+{
+    if (int rc = require_device()) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!frames || !layer_offsets)) || !bg_color)
+        return set_error(MVB_ERR_INVALID_ARG, "bad frames / layer_offsets / bg_color");
+    for (int f = 0; f < n_frames; f++) {
+        if (int rc = check_image(frames[f], W, H, stride, "frame")) return rc;
+        const int n = layer_offsets[f + 1] - layer_offsets[f];
+        if (n < 0 || (n > 0 && !layers)) return set_error(MVB_ERR_INVALID_ARG, "layer_offsets must be non-decreasing");
+        if (int rc = launch_stack(frames[f], W, H, stride, bg_color, n, layers + layer_offsets[f], flags,
+                                  (cudaStream_t)stream))
+            return rc;
+    }
+    return MVB_OK;
+}
+
+extern "C" int mvb_warp_affine_rgba8(const void* src, int32_t sw, int32_t sh, int64_t sstride, void* dst,
+                                     int32_t dw, int32_t dh, int64_t dstride, const double M[6],
+                                     mvb_stream_t stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_image(src, sw, sh, sstride, "src")) return rc;
+    if (int rc = check_image(dst, dw, dh, dstride, "dst")) return rc;
+    if (!M || sw >= 32768 || sh >= 32768) return set_error(MVB_ERR_INVALID_ARG, "bad matrix or source too large");
+    double m[6];
+    invert_affine_cv(M, m);
+    const dim3 grid((dw + 31) / 32, (dh + 7) / 8);
+    k_warp_affine<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint8_t*>(src), sw, sh, (int)sstride, static_cast<uint8_t*>(dst), dw, dh,
+        (int)dstride, m[0], m[1], m[2], m[3], m[4], m[5]);
+    return check_launch("mvb_warp_affine_rgba8");
+}
+
+extern "C" int mvb_alpha_composite(void* bg, int32_t bw, int32_t bh, int64_t bstride, const void* fg, int32_t fw,
+                                   int32_t fh, int64_t fstride, int32_t px, int32_t py, double opacity,
+                                   int32_t blend_mode, int32_t matte_mode, int32_t flags, mvb_stream_t stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_image(bg, bw, bh, bstride, "bg")) return rc;
+    if (int rc = check_image(fg, fw, fh, fstride, "fg")) return rc;
+    if (blend_mode < 0 || blend_mode >= MVB_BLEND_COUNT || matte_mode < 0 || matte_mode > 2)
+        return set_error(MVB_ERR_INVALID_ARG, "unknown blend or matte mode");
+    if (!(opacity >= 0.0 && opacity <= 1.0)) return set_error(MVB_ERR_INVALID_ARG, "opacity must be in [0, 1]");
+    const bool pil = (flags & MVB_LAYER_PIL_OVER) != 0;
+    if (pil && (blend_mode != MVB_BLEND_NORMAL || matte_mode != MVB_MATTE_NONE))
+        return set_error(MVB_ERR_INVALID_ARG, "MVB_LAYER_PIL_OVER requires NORMAL blending and no matte");
+    OverParams P;
+    P.bg = static_cast<uint8_t*>(bg);
+    P.bw = bw; P.bh = bh; P.bstride = (int32_t)bstride;
+    P.fg = static_cast<const uint8_t*>(fg);
+    P.fstride = (int32_t)fstride;
+    P.x1 = px > 0 ? px : 0; P.y1 = py > 0 ? py : 0;
+    P.x2 = px < 0 ? -px : 0; P.y2 = py < 0 ? -py : 0;
+    const int64_t w = (int64_t)(px + (int64_t)fw < bw ? px + (int64_t)fw : bw) - P.x1;
+    const int64_t h = (int64_t)(py + (int64_t)fh < bh ? py + (int64_t)fh : bh) - P.y1;
+    if (w <= 0 || h <= 0) return MVB_OK; // imgproc.py:189-190 (and PIL's clipped paste)
+    P.w = (int32_t)w; P.h = (int32_t)h;
+    P.mode = blend_mode; P.matte = matte_mode; P.pil = pil ? 1 : 0;
+    P.pil_a = (int32_t)std::nearbyint(opacity * 255.0);
+    P.opacity = opacity;
+    const bool lum = matte_mode == MVB_MATTE_LUMINANCE;
+    const dim3 grid(((lum ? bw : P.w) + 31) / 32, ((lum ? bh : P.h) + 7) / 8);
+    k_alpha_composite<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    return check_launch("mvb_alpha_composite");
+}

@@ -1,0 +1,501 @@
+// effects.cu -- GaussianBlur / Glow / DropShadow (separable Q8.8 -> Q16.16 fixed point) and the
+// pointwise colour effects ChromaKey / FillColor / HSLShift (sm_100a).  C ABI in
+// include/movis_b200.h; arithmetic contract in SURVEY.md 8(a)-7..10 and oracle/mvo.c.
+//
+// Blur layout.  The reference pads the layer by k px per side (RGB edge-replicated, alpha 0) and
+// blurs the padded image with cv2.GaussianBlur (reflect-101 border).  Because the pad is wider
+// than the kernel radius, that equals blurring a *virtual* image whose RGB is the source clamped
+// to its edge and whose alpha is 0 outside the source -- so no padded copy is ever materialised:
+//   H pass:  mid[y][X] = sum_j w[j] * tap(X + j - r - k, y)        for the h source rows only
+//            (uint16 x C per pixel: sum w = 256 keeps it inside 16 bits)
+//   V pass:  out[Y][X] = (sum_i w[i] * mid[clamp(Y + i - r - k)][X] + 32768) >> 16
+//            (alpha rows outside the source contribute 0), with the Glow composite fused in.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/movis_b200.h"
+#include "host_util.h"
+#include "pixel_math.cuh"
+
+namespace mvb {
+
+constexpr int kMaxKsize = 1023; // weights travel as kernel parameters
+
+struct BlurParams {
+    const uint8_t* src;
+    int32_t w, h, sstride;
+    int32_t k;          // ksize (odd); pad == k
+    uint16_t* mid;      // h x (w + 2k) x C uint16
+    uint8_t* dst;       // (h + 2k) x (w + 2k), RGBA8 (C == 4) or 1 byte per pixel (C == 1)
+    int32_t dstride;
+    int32_t mode;       // MVB_BLUR_PLAIN / MVB_BLUR_GLOW
+    uint8_t lut[256];   // glow strength LUT
+    uint16_t wt[kMaxKsize + 1];
+};
+
+// H pass, RGBA.  One thread per (X, source row).
+__global__ void __launch_bounds__(256) k_blur_h_rgba(const __grid_constant__ BlurParams P)
+{
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int W2 = P.w + 2 * P.k;
+    if (X >= W2 || y >= P.h) return;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(P.src + (int64_t)y * P.sstride);
+    const int r = P.k >> 1;
+    const int x0 = X - r - P.k; // source x of tap 0
+    uint32_t ar = 0, ag = 0, ab = 0, aa = 0;
+    for (int j = 0; j < P.k; j++) {
+        const int sx = x0 + j;
+        const uint32_t p = __ldg(row + min(max(sx, 0), P.w - 1));
+        const uint32_t wj = P.wt[j];
+        ar += wj * (p & 0xFFu);
+        ag += wj * ((p >> 8) & 0xFFu);
+        ab += wj * ((p >> 16) & 0xFFu);
+        if ((unsigned)sx < (unsigned)P.w) aa += wj * (p >> 24);
+    }
+    uint2 o;
+    o.x = ar | (ag << 16);
+    o.y = ab | (aa << 16);
+    reinterpret_cast<uint2*>(P.mid)[(int64_t)y * W2 + X] = o;
+}
+
+// V pass, RGBA (+ fused Glow composite).  One thread per output pixel.
+__global__ void __launch_bounds__(256) k_blur_v_rgba(const __grid_constant__ BlurParams P)
+{
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int W2 = P.w + 2 * P.k, H2 = P.h + 2 * P.k;
+    if (X >= W2 || Y >= H2) return;
+    const uint2* mid = reinterpret_cast<const uint2*>(P.mid);
+    const int r = P.k >> 1;
+    const int y0 = Y - r - P.k;
+    uint32_t ar = 0, ag = 0, ab = 0, aa = 0;
+    for (int i = 0; i < P.k; i++) {
+        const int sy = y0 + i;
+        const uint2 m = __ldg(mid + (int64_t)min(max(sy, 0), P.h - 1) * W2 + X);
+        const uint32_t wi = P.wt[i];
+        ar += wi * (m.x & 0xFFFFu);
+        ag += wi * (m.x >> 16);
+        ab += wi * (m.y & 0xFFFFu);
+        if ((unsigned)sy < (unsigned)P.h) aa += wi * (m.y >> 16);
+    }
+    Rgba s{(ar + 32768u) >> 16, (ag + 32768u) >> 16, (ab + 32768u) >> 16, (aa + 32768u) >> 16};
+    uint32_t o;
+    if (P.mode == MVB_BLUR_GLOW) {
+        // pad_image pixel (blur.py:74-76): rgb edge-replicated, alpha 0 outside the source
+        const int sx = X - P.k, sy = Y - P.k;
+        uint32_t d = __ldg(reinterpret_cast<const uint32_t*>(P.src + (int64_t)min(max(sy, 0), P.h - 1) * P.sstride) +
+                           min(max(sx, 0), P.w - 1));
+        if ((unsigned)sx >= (unsigned)P.w || (unsigned)sy >= (unsigned)P.h) d &= 0x00FFFFFFu;
+        s.r = P.lut[s.r]; s.g = P.lut[s.g]; s.b = P.lut[s.b]; // blur.py:82
+        o = over_numpy<MVB_BLEND_LINEAR_DODGE>(d, s, s.a, false); // blur.py:84-85
+    } else {
+        o = pack(s.r, s.g, s.b, s.a);
+    }
+    reinterpret_cast<uint32_t*>(P.dst + (int64_t)Y * P.dstride)[X] = o;
+}
+
+// H / V passes on the alpha channel only (DropShadow, style.py:60-62): zero padding.
+__global__ void __launch_bounds__(256) k_blur_h_alpha(const __grid_constant__ BlurParams P)
+{
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int W2 = P.w + 2 * P.k;
+    if (X >= W2 || y >= P.h) return;
+    const uint8_t* row = P.src + (int64_t)y * P.sstride + 3;
+    const int r = P.k >> 1;
+    const int x0 = X - r - P.k;
+    uint32_t aa = 0;
+    for (int j = 0; j < P.k; j++) {
+        const int sx = x0 + j;
+        if ((unsigned)sx < (unsigned)P.w) aa += (uint32_t)P.wt[j] * row[(int64_t)sx * 4];
+    }
+    P.mid[(int64_t)y * W2 + X] = (uint16_t)aa;
+}
+
+__global__ void __launch_bounds__(256) k_blur_v_alpha(const __grid_constant__ BlurParams P)
+{
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int W2 = P.w + 2 * P.k, H2 = P.h + 2 * P.k;
+    if (X >= W2 || Y >= H2) return;
+    const int r = P.k >> 1;
+    const int y0 = Y - r - P.k;
+    uint32_t aa = 0;
+    for (int i = 0; i < P.k; i++) {
+        const int sy = y0 + i;
+        if ((unsigned)sy < (unsigned)P.h) aa += (uint32_t)P.wt[i] * P.mid[(int64_t)sy * W2 + X];
+    }
+    P.dst[(int64_t)Y * P.dstride + X] = (uint8_t)((aa + 32768u) >> 16);
+}
+
+struct ShadowParams {
+    const uint8_t* src;
+    int32_t w, h, sstride;
+    const uint8_t* a1;  // blurred alpha plane (Ws x Hs) or nullptr when k == 0
+    int32_t Ws, Hs;
+    uint8_t* dst;
+    int32_t Wn, Hn, dstride;
+    int32_t sx0, sy0;   // where the shadow is pasted (style.py:79-80)
+    int32_t px, py;     // where the original is composited (style.py:83)
+    uint32_t color;     // packed rgb
+    uint8_t lut[256];   // uint8(opacity * v)
+};
+
+// DropShadow assembly (style.py:64-84): shadow pixel, then PIL-over of the original at the centre.
+__global__ void __launch_bounds__(256) k_drop_shadow(const __grid_constant__ ShadowParams P)
+{
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (X >= P.Wn || Y >= P.Hn) return;
+    uint32_t d = 0;
+    const int xs = X - P.sx0, ys = Y - P.sy0;
+    if ((unsigned)xs < (unsigned)P.Ws && (unsigned)ys < (unsigned)P.Hs) {
+        uint32_t a;
+        if (P.a1) a = P.a1[(int64_t)ys * P.Ws + xs];
+        else a = P.lut[P.src[(int64_t)ys * P.sstride + (int64_t)xs * 4 + 3]]; // style.py:64 (radius == 0)
+        d = P.color | ((uint32_t)P.lut[a] << 24);                                // style.py:68
+    }
+    const int xo = X - P.px, yo = Y - P.py;
+    if ((unsigned)xo < (unsigned)P.w && (unsigned)yo < (unsigned)P.h) {
+        const uint32_t spx = __ldg(reinterpret_cast<const uint32_t*>(P.src + (int64_t)yo * P.sstride) + xo);
+        const Rgba s = unpack(spx);
+        d = over_pil(d, s, s.a);
+    }
+    reinterpret_cast<uint32_t*>(P.dst + (int64_t)Y * P.dstride)[X] = d;
+}
+
+// ---- colour conversions -----------------------------------------------------------------------
+
+struct HsvTables { int32_t sdiv[256]; int32_t hdiv[256]; };
+__constant__ HsvTables c_hsv;
+
+// cv2.COLOR_RGB2HSV, 8-bit, H in [0, 180)
+__device__ __forceinline__ void rgb_to_hsv(int r, int g, int b, const int32_t* sdiv, const int32_t* hdiv,
+                                           int& h, int& s, int& v)
+{
+    v = max(max(r, g), b);
+    const int vmin = min(min(r, g), b);
+    const int diff = v - vmin;
+    s = (diff * sdiv[v] + (1 << 11)) >> 12;
+    int hh;
+    if (v == r) hh = g - b;
+    else if (v == g) hh = b - r + 2 * diff;
+    else hh = r - g + 4 * diff;
+    hh = (hh * hdiv[diff] + (1 << 11)) >> 12;
+    if (hh < 0) hh += 180;
+    h = min(max(hh, 0), 255);
+}
+
+// cv2.COLOR_HSV2RGB, 8-bit: float32 sector formula with one fused multiply-add per tab entry;
+// `round_result` selects the rounding cv2 applies in the scalar tail of a row (see oracle/mvo.c).
+__device__ __forceinline__ uint32_t hsv_to_rgb(int hi, int si, int vi, bool round_result)
+{
+    const float s = __fmul_rn((float)si, 1.0f / 255.0f), v = __fmul_rn((float)vi, 1.0f / 255.0f);
+    float r, g, b;
+    if (si == 0) {
+        r = g = b = v;
+    } else {
+        float h = __fmul_rn((float)hi, 6.0f / 180.0f);
+        int sector = (int)floorf(h);
+        h = __fsub_rn(h, (float)sector);
+        sector %= 6;
+        const float t1 = __fmul_rn(v, __fsub_rn(1.0f, s));
+        const float t2 = __fmul_rn(v, __fmaf_rn(-s, h, 1.0f));
+        const float t3 = __fmul_rn(v, __fmaf_rn(-s, __fsub_rn(1.0f, h), 1.0f));
+        switch (sector) { // sector_data of cv::HSV2RGB_native, (b, g, r) rows
+        case 0: b = t1; g = t3; r = v; break;
+        case 1: b = t1; g = v; r = t2; break;
+        case 2: b = t3; g = v; r = t1; break;
+        case 3: b = v; g = t2; r = t1; break;
+        case 4: b = v; g = t1; r = t3; break;
+        default: b = t2; g = t1; r = v; break;
+        }
+    }
+    r = __fmul_rn(r, 255.0f); g = __fmul_rn(g, 255.0f); b = __fmul_rn(b, 255.0f);
+    int ri, gi, bi;
+    if (round_result) { ri = __float2int_rn(r); gi = __float2int_rn(g); bi = __float2int_rn(b); }
+    else { ri = __float2int_rz(r); gi = __float2int_rz(g); bi = __float2int_rz(b); }
+    return (uint32_t)min(max(ri, 0), 255) | ((uint32_t)min(max(gi, 0), 255) << 8) |
+           ((uint32_t)min(max(bi, 0), 255) << 16);
+}
+
+struct PointParams {
+    const uint8_t* src;
+    uint8_t* dst;
+    int32_t w, h, sstride, dstride;
+    int32_t op;          // 0 chroma key, 1 fill colour, 2 HSL shift
+    uint32_t color;      // fill colour (packed rgb)
+    uint8_t lo[4], hi[4];
+    uint8_t hlut[256], slut[256], vlut[256];
+};
+
+__global__ void __launch_bounds__(256) k_pointwise(const __grid_constant__ PointParams P)
+{
+    __shared__ int32_t s_sdiv[256], s_hdiv[256];
+    if (P.op != 1) {
+        s_sdiv[threadIdx.x] = c_hsv.sdiv[threadIdx.x];
+        s_hdiv[threadIdx.x] = c_hsv.hdiv[threadIdx.x];
+        __syncthreads();
+    }
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.w || y >= P.h) return;
+    const uint32_t p = reinterpret_cast<const uint32_t*>(P.src + (int64_t)y * P.sstride)[x];
+    uint32_t o;
+    if (P.op == 1) {
+        o = P.color | (p & 0xFF000000u);
+    } else {
+        int hh, ss, vv;
+        rgb_to_hsv(p & 0xFF, (p >> 8) & 0xFF, (p >> 16) & 0xFF, s_sdiv, s_hdiv, hh, ss, vv);
+        if (P.op == 0) {
+            const bool in = hh >= P.lo[0] && hh <= P.hi[0] && ss >= P.lo[1] && ss <= P.hi[1] &&
+                            vv >= P.lo[2] && vv <= P.hi[2];
+            o = (p & 0x00FFFFFFu) | (in ? 0u : 0xFF000000u);
+        } else {
+            const bool tail = x >= P.w - (P.w & 31);
+            o = hsv_to_rgb(P.hlut[hh], P.slut[ss], P.vlut[vv], tail) | (p & 0xFF000000u);
+        }
+    }
+    reinterpret_cast<uint32_t*>(P.dst + (int64_t)y * P.dstride)[x] = o;
+}
+
+// ---- host side --------------------------------------------------------------------------------
+
+static void host_hsv_tables(HsvTables& t)
+{
+    t.sdiv[0] = t.hdiv[0] = 0;
+    for (int i = 1; i < 256; i++) {
+        t.sdiv[i] = (int32_t)std::nearbyint((255 << 12) / (1. * i));
+        t.hdiv[i] = (int32_t)std::nearbyint((180 << 12) / (6. * i));
+    }
+}
+
+static int upload_hsv_tables()
+{
+    static thread_local int uploaded_dev = -1;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev == uploaded_dev) return MVB_OK;
+    HsvTables t;
+    host_hsv_tables(t);
+    cudaError_t e = cudaMemcpyToSymbol(c_hsv, &t, sizeof t);
+    if (e != cudaSuccess) return set_error(MVB_ERR_CUDA, cudaGetErrorString(e));
+    uploaded_dev = dev;
+    return MVB_OK;
+}
+
+static int check_rgba(const void* p, int w, int h, int64_t stride, const char* what)
+{
+    if (!p || w <= 0 || h <= 0 || stride < (int64_t)w * 4 || (stride & 3) || stride > 0x7FFFFFFF ||
+        (reinterpret_cast<uintptr_t>(p) & 3)) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "%s: need non-null 4-byte-aligned RGBA8 image with stride >= 4*width", what);
+        return set_error(MVB_ERR_INVALID_ARG, buf);
+    }
+    return 0;
+}
+
+static int check_ksize(int k, const uint16_t* weights)
+{
+    if (k < 3 || !(k & 1) || k > kMaxKsize)
+        return set_error(MVB_ERR_UNSUPPORTED, "ksize must be odd and in [3, 1023]");
+    if (!weights) return set_error(MVB_ERR_INVALID_ARG, "weights is null");
+    return 0;
+}
+
+} // namespace mvb
+
+using namespace mvb;
+
+extern "C" int mvb_blur_ksize(double radius)
+{
+    double v = (4 * radius - 1) / 2;
+    if (v < 1) v = 1;
+    return 2 * (int)std::ceil(v) + 1;
+}
+
+extern "C" int mvb_gaussian_weights_q8(double sigma, int32_t k, uint16_t* w)
+{
+    if (!(sigma > 0) || k < 1 || !(k & 1) || !w) return set_error(MVB_ERR_INVALID_ARG, "need sigma > 0, odd ksize");
+    // cv::getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED(fractionBits = 8) in IEEE double
+    const int n2 = (k - 1) / 2;
+    std::vector<double> val((size_t)n2 + 1);
+    const double scale2X = -0.125 / (sigma * sigma);
+    double sum = 0;
+    for (int i = 0, x = 1 - k; i < n2; i++, x += 2) {
+        const double t = std::exp((double)(x * x) * scale2X);
+        val[i] = t;
+        sum += t;
+    }
+    sum *= 2;
+    sum += 1;
+    const double mul1 = 1.0 / sum;
+    double err = 0;
+    int64_t isum = 0;
+    for (int i = 0; i < n2; i++) {
+        const double adj = (val[i] * mul1) * 256.0 + err;
+        const int64_t v0 = (int64_t)std::nearbyint(adj);
+        err = adj - (double)v0;
+        w[i] = w[k - 1 - i] = (uint16_t)v0;
+        isum += v0;
+    }
+    w[n2] = (uint16_t)(256 - 2 * isum);
+    return MVB_OK;
+}
+
+extern "C" size_t mvb_effect_blur_scratch_bytes(int32_t w, int32_t h, int32_t k, int32_t channels)
+{
+    if (w <= 0 || h <= 0 || k < 0 || (channels != 1 && channels != 4)) return 0;
+    size_t b = (size_t)h * (size_t)(w + 2 * k) * (size_t)channels * 2;
+    return (b + 255) & ~(size_t)255;
+}
+
+extern "C" int mvb_effect_blur_rgba8(const void* src, int32_t w, int32_t h, int64_t sstride, void* dst,
+                                     int64_t dstride, int32_t k, const uint16_t* weights, int32_t mode,
+                                     const uint8_t* strength_lut, void* scratch, mvb_stream_t stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_rgba(src, w, h, sstride, "src")) return rc;
+    if (int rc = check_ksize(k, weights)) return rc;
+    if (int rc = check_rgba(dst, w + 2 * k, h + 2 * k, dstride, "dst")) return rc;
+    if (!scratch || (reinterpret_cast<uintptr_t>(scratch) & 7)) return set_error(MVB_ERR_INVALID_ARG, "scratch must be 8-byte aligned");
+    if (mode != MVB_BLUR_PLAIN && mode != MVB_BLUR_GLOW) return set_error(MVB_ERR_INVALID_ARG, "unknown blur mode");
+    if (mode == MVB_BLUR_GLOW && !strength_lut) return set_error(MVB_ERR_INVALID_ARG, "glow needs strength_lut");
+    BlurParams P;
+    P.src = static_cast<const uint8_t*>(src);
+    P.w = w; P.h = h; P.sstride = (int32_t)sstride; P.k = k;
+    P.mid = static_cast<uint16_t*>(scratch);
+    P.dst = static_cast<uint8_t*>(dst);
+    P.dstride = (int32_t)dstride;
+    P.mode = mode;
+    if (strength_lut) std::memcpy(P.lut, strength_lut, 256); else std::memset(P.lut, 0, 256);
+    std::memcpy(P.wt, weights, sizeof(uint16_t) * (size_t)k);
+    const int W2 = w + 2 * k, H2 = h + 2 * k;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_blur_h_rgba<<<dim3((W2 + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
+    k_blur_v_rgba<<<dim3((W2 + 31) / 32, (H2 + 7) / 8), 256, 0, st>>>(P);
+    return check_launch("mvb_effect_blur_rgba8");
+}
+
+extern "C" int mvb_effect_drop_shadow_rgba8(const void* src, int32_t w, int32_t h, int64_t sstride, void* dst,
+                                            int64_t dstride, int32_t k, const uint16_t* weights,
+                                            const uint8_t* opacity_lut, const uint8_t color[3], int32_t vx,
+                                            int32_t vy, void* scratch, mvb_stream_t stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_rgba(src, w, h, sstride, "src")) return rc;
+    if (k != 0) if (int rc = check_ksize(k, weights)) return rc;
+    if (!opacity_lut || !color) return set_error(MVB_ERR_INVALID_ARG, "opacity_lut / color is null");
+    const int Ws = w + 2 * k, Hs = h + 2 * k;
+    const int dx = vx < 0 ? -vx : vx, dy = vy < 0 ? -vy : vy;
+    const int Wn = Ws + 2 * dx, Hn = Hs + 2 * dy;
+    if (int rc = check_rgba(dst, Wn, Hn, dstride, "dst")) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ShadowParams S;
+    S.a1 = nullptr;
+    if (k != 0) {
+        if (!scratch || (reinterpret_cast<uintptr_t>(scratch) & 7)) return set_error(MVB_ERR_INVALID_ARG, "scratch must be 8-byte aligned");
+        BlurParams P;
+        P.src = static_cast<const uint8_t*>(src);
+        P.w = w; P.h = h; P.sstride = (int32_t)sstride; P.k = k;
+        P.mid = static_cast<uint16_t*>(scratch);
+        uint8_t* plane = static_cast<uint8_t*>(scratch) + mvb_effect_blur_scratch_bytes(w, h, k, 1);
+        P.dst = plane;
+        P.dstride = Ws;
+        P.mode = MVB_BLUR_PLAIN;
+        std::memset(P.lut, 0, 256);
+        std::memcpy(P.wt, weights, sizeof(uint16_t) * (size_t)k);
+        k_blur_h_alpha<<<dim3((Ws + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
+        k_blur_v_alpha<<<dim3((Ws + 31) / 32, (Hs + 7) / 8), 256, 0, st>>>(P);
+        S.a1 = plane;
+    }
+    S.src = static_cast<const uint8_t*>(src);
+    S.w = w; S.h = h; S.sstride = (int32_t)sstride;
+    S.Ws = Ws; S.Hs = Hs;
+    S.dst = static_cast<uint8_t*>(dst);
+    S.Wn = Wn; S.Hn = Hn; S.dstride = (int32_t)dstride;
+    S.sx0 = dx + vx; S.sy0 = dy + vy;
+    S.px = (Wn - w) / 2; S.py = (Hn - h) / 2;
+    S.color = (uint32_t)color[0] | ((uint32_t)color[1] << 8) | ((uint32_t)color[2] << 16);
+    std::memcpy(S.lut, opacity_lut, 256);
+    k_drop_shadow<<<dim3((Wn + 31) / 32, (Hn + 7) / 8), 256, 0, st>>>(S);
+    return check_launch("mvb_effect_drop_shadow_rgba8");
+}
+
+static int launch_pointwise(PointParams& P, const void* src, int w, int h, int64_t sstride, void* dst,
+                            int64_t dstride, mvb_stream_t stream, const char* what)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_rgba(src, w, h, sstride, "src")) return rc;
+    if (int rc = check_rgba(dst, w, h, dstride, "dst")) return rc;
+    if (P.op != 1) if (int rc = upload_hsv_tables()) return rc;
+    P.src = static_cast<const uint8_t*>(src);
+    P.dst = static_cast<uint8_t*>(dst);
+    P.w = w; P.h = h; P.sstride = (int32_t)sstride; P.dstride = (int32_t)dstride;
+    k_pointwise<<<dim3((w + 31) / 32, (h + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P);
+    return check_launch(what);
+}
+
+extern "C" int mvb_effect_chroma_key_rgba8(const void* src, int32_t w, int32_t h, int64_t sstride, void* dst,
+                                           int64_t dstride, const uint8_t lo[3], const uint8_t hi[3],
+                                           mvb_stream_t stream)
+{
+    if (!lo || !hi) return set_error(MVB_ERR_INVALID_ARG, "bounds are null");
+    PointParams P;
+    std::memset(&P, 0, sizeof P);
+    P.op = 0;
+    std::memcpy(P.lo, lo, 3);
+    std::memcpy(P.hi, hi, 3);
+    return launch_pointwise(P, src, w, h, sstride, dst, dstride, stream, "mvb_effect_chroma_key_rgba8");
+}
+
+extern "C" int mvb_effect_fill_color_rgba8(const void* src, int32_t w, int32_t h, int64_t sstride, void* dst,
+                                           int64_t dstride, const uint8_t color[3], mvb_stream_t stream)
+{
+    if (!color) return set_error(MVB_ERR_INVALID_ARG, "color is null");
+    PointParams P;
+    std::memset(&P, 0, sizeof P);
+    P.op = 1;
+    P.color = (uint32_t)color[0] | ((uint32_t)color[1] << 8) | ((uint32_t)color[2] << 16);
+    return launch_pointwise(P, src, w, h, sstride, dst, dstride, stream, "mvb_effect_fill_color_rgba8");
+}
+
+extern "C" int mvb_effect_hsl_shift_rgba8(const void* src, int32_t w, int32_t h, int64_t sstride, void* dst,
+                                          int64_t dstride, const uint8_t h_lut[256], const uint8_t s_lut[256],
+                                          const uint8_t v_lut[256], mvb_stream_t stream)
+{
+    if (!h_lut || !s_lut || !v_lut) return set_error(MVB_ERR_INVALID_ARG, "lut is null");
+    PointParams P;
+    std::memset(&P, 0, sizeof P);
+    P.op = 2;
+    std::memcpy(P.hlut, h_lut, 256);
+    std::memcpy(P.slut, s_lut, 256);
+    std::memcpy(P.vlut, v_lut, 256);
+    return launch_pointwise(P, src, w, h, sstride, dst, dstride, stream, "mvb_effect_hsl_shift_rgba8");
+}
+
+extern "C" int mvb_rgb_to_hsv_u8(const uint8_t rgb[3], uint8_t hsv[3])
+{
+    if (!rgb || !hsv) return set_error(MVB_ERR_INVALID_ARG, "null argument");
+    static HsvTables t;
+    static bool ready = false;
+    if (!ready) { host_hsv_tables(t); ready = true; }
+    const int r = rgb[0], g = rgb[1], b = rgb[2];
+    const int v = r > g ? (r > b ? r : b) : (g > b ? g : b);
+    const int vmin = r < g ? (r < b ? r : b) : (g < b ? g : b);
+    const int diff = v - vmin;
+    const int s = (diff * t.sdiv[v] + (1 << 11)) >> 12;
+    int h;
+    if (v == r) h = g - b;
+    else if (v == g) h = b - r + 2 * diff;
+    else h = r - g + 4 * diff;
+    h = (h * t.hdiv[diff] + (1 << 11)) >> 12;
+    if (h < 0) h += 180;
+    hsv[0] = (uint8_t)(h < 0 ? 0 : (h > 255 ? 255 : h));
+    hsv[1] = (uint8_t)s;
+    hsv[2] = (uint8_t)v;
+    return MVB_OK;
+}

@@ -1,0 +1,235 @@
+"""Parity of every C-ABI operator on the GPU: against the golden vectors recorded from the
+reference, and against the CPU oracle on seeded inputs.  Bar: bit-exact (uint8/integer work)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    from movis_b200 import _native
+    from movis_b200.device import image_args, stream_ptr, to_device
+
+    class D:
+        lib = _native.lib()
+        native = _native
+
+        @staticmethod
+        def up(a):
+            return to_device(np.ascontiguousarray(a))
+
+        @staticmethod
+        def down(t):
+            torch.cuda.synchronize()
+            return t.cpu().numpy()
+
+        args = staticmethod(image_args)
+        stream = staticmethod(stream_ptr)
+    assert D.lib.mvb_device_check() == 0, D.lib.mvb_last_error()
+    return D
+
+
+def _composite(dev, bg, fg, pos, op, mode, matte, pil=None):
+    import torch
+    if pil is None:
+        pil = (mode == 0 and matte == 0)
+    b, f = dev.up(bg), dev.up(fg)
+    bp, bw, bh, bs = dev.args(b)
+    fp, fw, fh, fs = dev.args(f)
+    dev.native.check(dev.lib.mvb_alpha_composite(bp, bw, bh, bs, fp, fw, fh, fs, int(pos[0]), int(pos[1]),
+                                                 float(op), int(mode), int(matte), 1 if pil else 0, dev.stream()))
+    return dev.down(b)
+
+
+def test_alpha_composite_golden(dev, golden):
+    g = golden("alpha_composite")
+    for i, (px, py, mode, matte) in enumerate(g["meta"]):
+        out = _composite(dev, g[f"bg{i}"], g[f"fg{i}"], (px, py), float(g[f"op{i}"]), mode, matte)
+        assert np.array_equal(out, g[f"out{i}"]), f"case {i}: mode {mode} matte {matte}"
+    out = _composite(dev, g["str_bg"], g["str_fg"], (3, 4), 0.6, 0, 0, pil=False)
+    assert np.array_equal(out, g["str_out"])
+
+
+def test_over_every_alpha_pair_golden(dev, golden):
+    g = golden("over_alpha_pairs")
+    bg, fg = g["bg"], g["fg"]
+    assert np.array_equal(_composite(dev, bg, fg, (0, 0), 1.0, 0, 0), g["pil_1"])
+    assert np.array_equal(_composite(dev, bg, fg, (0, 0), 0.37, 0, 0), g["pil_037"])
+    assert np.array_equal(_composite(dev, bg, fg, (0, 0), 1.0, 11, 0), g["soft_1"])
+    assert np.array_equal(_composite(dev, bg, fg, (0, 0), 0.37, 1, 0), g["mult_037"])
+
+
+def test_every_mode_every_channel_pair_vs_oracle(dev):
+    """All 65 536 (bg, fg) channel values x 18 modes x {opaque, translucent, transparent} bg alpha."""
+    from oracle import oracle as O
+    b = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 256, 1)
+    f = np.repeat(np.arange(256, dtype=np.uint8)[None, :], 256, 0)
+    rng = np.random.default_rng(0)
+    for ba in (255, 200, 0):
+        bg = np.stack([b, b, b, np.full_like(b, ba)], -1)
+        fg = np.stack([f, f, f, rng.integers(0, 256, b.shape, dtype=np.uint8)], -1)
+        for mode in range(18):
+            for matte in (0, 1):
+                want = O.alpha_composite(bg, fg, (0, 0), 0.8, mode, matte, use_pil=False)
+                got = _composite(dev, bg, fg, (0, 0), 0.8, mode, matte, pil=False)
+                assert np.array_equal(got, want), (ba, mode, matte)
+
+
+def test_alpha_composite_fuzz_vs_oracle(dev):
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    for i in range(120):
+        bg = rng.integers(0, 256, tuple(rng.integers(1, 70, 2)) + (4,), dtype=np.uint8)
+        fg = rng.integers(0, 256, tuple(rng.integers(1, 70, 2)) + (4,), dtype=np.uint8)
+        if i % 2:
+            bg[..., 3] = rng.choice([0, 1, 254, 255], size=bg.shape[:2])
+        if i % 3 == 0:
+            fg[..., 3] = rng.choice([0, 1, 254, 255], size=fg.shape[:2])
+        pos = rng.integers(-60, 60, 2)
+        op = [1.0, 0.0, float(rng.uniform())][i % 3]
+        mode, matte = i % 18, (i // 18) % 3
+        want = O.alpha_composite(bg, fg, pos, op, mode, matte)
+        got = _composite(dev, bg, fg, pos, op, mode, matte)
+        assert np.array_equal(got, want), (i, mode, matte)
+
+
+def _warp(dev, src, M, dsize):
+    import torch
+    s = dev.up(src)
+    d = torch.empty((dsize[1], dsize[0], 4), dtype=torch.uint8, device="cuda")
+    sp, sw, sh, ss = dev.args(s)
+    Mf = np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(6))
+    dev.native.check(dev.lib.mvb_warp_affine_rgba8(sp, sw, sh, ss, d.data_ptr(), dsize[0], dsize[1], d.stride(0),
+                                                   Mf.ctypes.data, dev.stream()))
+    return dev.down(d)
+
+
+def test_warp_affine_golden(dev, golden):
+    g = golden("warp_affine")
+    for i, (M, dsize) in enumerate(zip(g["M"], g["dsize"])):
+        out = _warp(dev, g[f"src{i}"], M, (int(dsize[0]), int(dsize[1])))
+        assert np.array_equal(out, g[f"dst{i}"]), f"case {i}"
+
+
+def test_warp_affine_large_vs_oracle(dev):
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (1080, 1920, 4), dtype=np.uint8)
+    for ang, s, tx, ty in [(13.3, 1.17, 400.3, 100.7), (-170.0, 0.45, 1500.0, 900.25), (0.0, 1.0, 0.5, 0.5)]:
+        a = np.deg2rad(ang)
+        M = np.array([[s * np.cos(a), -s * np.sin(a), tx], [s * np.sin(a), s * np.cos(a), ty]])
+        assert np.array_equal(_warp(dev, src, M, (2560, 1848)), O.warp_affine(src, M, (2560, 1848)))
+    # a non-contiguous source view (ops.crop hands those out, ops.py:296): explicit row stride
+    import torch
+    big = dev.up(src)
+    view = big[100:600, 200:900]
+    d = torch.empty((300, 400, 4), dtype=torch.uint8, device="cuda")
+    M = np.array([[0.7, 0.2, 10.0], [-0.2, 0.7, 50.0]])
+    dev.native.check(dev.lib.mvb_warp_affine_rgba8(view.data_ptr(), 700, 500, view.stride(0), d.data_ptr(), 400, 300,
+                                                   d.stride(0), np.ascontiguousarray(M.reshape(6)).ctypes.data,
+                                                   dev.stream()))
+    assert np.array_equal(dev.down(d), O.warp_affine(src[100:600, 200:900], M, (400, 300)))
+
+
+def test_effects_golden(dev, golden):
+    import movis_b200 as mv
+    from movis_b200.contrib.segmentation import ChromaKey
+    g = golden("effects")
+    for i, p in enumerate(g["params"]):
+        r, st, off, ang, op = (float(v) for v in p[:5])
+        col = tuple(int(v) for v in p[5:8])
+        hu, sat, lum = (float(v) for v in p[8:11])
+        krange = tuple(float(v) for v in p[11:14])
+        img = g[f"img{i}"]
+        for name, eff, src in [
+            ("blur", mv.effect.GaussianBlur(r), img), ("glow", mv.effect.Glow(r, st), img),
+            ("shadow", mv.effect.DropShadow(r, off, ang, col, op), img), ("fill", mv.effect.FillColor(col), img),
+            ("hsl", mv.effect.HSLShift(hu, sat, lum), img),
+            ("chroma", ChromaKey(col, key_color_range=krange), g[f"keyed{i}"]),
+        ]:
+            got = eff(src, 0.0)
+            assert isinstance(got, np.ndarray) and got.dtype == np.uint8
+            assert got.shape == g[f"{name}{i}"].shape, (name, i)
+            assert np.array_equal(got, g[f"{name}{i}"]), (name, i)
+    blue = np.zeros((4, 4, 4), np.uint8)
+    blue[..., 2] = 255
+    blue[..., 3] = 255
+    assert np.array_equal(mv.effect.HSLShift(hue=180.0)(blue, 0.0), g["hsl_blue_180"])
+
+
+def test_blur_family_vs_oracle_all_radii(dev):
+    import movis_b200 as mv
+    from oracle import oracle as O
+    rng = np.random.default_rng(9)
+    for r in [0.3, 0.5, 1.0, 2.0, 3.3, 7.7, 10.0, 17.2, 25.0]:
+        img = rng.integers(0, 256, tuple(rng.integers(8, 90, 2)) + (4,), dtype=np.uint8)
+        assert np.array_equal(mv.effect.GaussianBlur(r)(img, 0.0), O.effect_gaussian_blur(img, r)), r
+        assert np.array_equal(mv.effect.Glow(r, 1.3)(img, 0.0), O.effect_glow(img, r, 1.3)), r
+        assert np.array_equal(mv.effect.DropShadow(r, 20.0, 45.0, (9, 8, 7), 0.5)(img, 0.0),
+                              O.effect_drop_shadow(img, r, 20.0, 45.0, (9, 8, 7), 0.5)), r
+    img = rng.integers(0, 256, (400, 400, 4), dtype=np.uint8)  # config-3 sized
+    assert np.array_equal(mv.effect.GaussianBlur(10.0)(img, 0.0), O.effect_gaussian_blur(img, 10.0))
+
+
+def test_pointwise_effects_vs_oracle_ragged_widths(dev):
+    import movis_b200 as mv
+    from movis_b200.contrib.segmentation import ChromaKey
+    from oracle import oracle as O
+    rng = np.random.default_rng(10)
+    for w in (1, 31, 32, 33, 95, 100, 257):
+        img = rng.integers(0, 256, (7, w, 4), dtype=np.uint8)
+        img[:3, :, :3] = (0, 255, 0)
+        assert np.array_equal(mv.effect.HSLShift(77.0, -0.2, 0.3)(img, 0.0), O.effect_hsl_shift(img, 77.0, -0.2, 0.3)), w
+        assert np.array_equal(ChromaKey()(img, 0.0), O.effect_chroma_key(img)), w
+    full = rng.integers(0, 256, (2160, 3840, 4), dtype=np.uint8)  # config-4 sized green screen
+    full[:1080, :, :3] = (0, 255, 0)
+    got = ChromaKey()(full, 0.0)
+    assert np.array_equal(got, O.effect_chroma_key(full))
+    assert (got[:1080, :, 3] == 0).all() and set(np.unique(got[..., 3])) <= {0, 255}
+
+
+def test_public_alpha_composite_semantics(dev):
+    import torch
+    import movis_b200 as mv
+    from oracle import oracle as O
+    rng = np.random.default_rng(2)
+    bg = rng.integers(0, 256, (20, 30, 4), dtype=np.uint8)
+    fg = rng.integers(0, 256, (10, 10, 4), dtype=np.uint8)
+    keep = bg.copy()
+    out = mv.alpha_composite(bg, fg, (5, 5), 0.5)                       # PIL path: new array
+    assert np.array_equal(bg, keep) and out is not bg
+    assert np.array_equal(out, O.alpha_composite(keep, fg, (5, 5), 0.5))
+    out = mv.alpha_composite(bg, fg, (5, 5), 0.5, "screen")             # numpy path: in place
+    assert out is bg and np.array_equal(bg, O.alpha_composite(keep, fg, (5, 5), 0.5, "screen"))
+    ro = keep.copy()
+    ro.flags.writeable = False
+    out = mv.alpha_composite(ro, fg, (5, 5), 0.5, mv.BlendingMode.SCREEN)
+    assert np.array_equal(ro, keep) and np.array_equal(out, bg)
+    out = mv.alpha_composite(keep.copy(), fg, (5, 5), 0.5, "normal")     # str 'normal' -> numpy arithmetic
+    assert np.array_equal(out, O.alpha_composite(keep, fg, (5, 5), 0.5, "normal", use_pil=False))
+    with pytest.raises(ValueError):
+        mv.alpha_composite(keep.copy(), fg, blending_mode="nope")
+    with pytest.raises(AssertionError):
+        mv.alpha_composite(keep[..., :3], fg)
+    with pytest.raises(AssertionError):
+        mv.alpha_composite(keep.copy(), fg, opacity=1.5)
+    tb, tf = torch.from_numpy(keep).cuda(), torch.from_numpy(fg).cuda()
+    out = mv.alpha_composite(tb, tf, (5, 5), 0.5, "multiply")
+    assert out is tb and np.array_equal(out.cpu().numpy(), O.alpha_composite(keep, fg, (5, 5), 0.5, "multiply"))
+
+
+def test_invalid_arguments_are_rejected(dev):
+    import torch
+    t = torch.zeros((8, 8, 4), dtype=torch.uint8, device="cuda")
+    bg = np.zeros(4, np.uint8)
+    lay = np.zeros(1, dtype=dev.native.LAYER_DTYPE)
+    lay["bbox_w"], lay["bbox_h"], lay["src_w"], lay["src_h"], lay["src_stride"] = 4, 4, 4, 4, 16
+    rc = dev.lib.mvb_composite_stack(t.data_ptr(), 8, 8, 32, bg.ctypes.data, 1, lay.ctypes.data, 0, dev.stream())
+    assert rc == -1 and b"source" in dev.lib.mvb_last_error()           # null src
+    lay["src"] = t.data_ptr()
+    lay["blend_mode"] = 99
+    assert dev.lib.mvb_composite_stack(t.data_ptr(), 8, 8, 32, bg.ctypes.data, 1, lay.ctypes.data, 0, dev.stream()) == -1
+    assert dev.lib.mvb_composite_stack(t.data_ptr(), 8, 8, 30, bg.ctypes.data, 0, None, 0, dev.stream()) == -1
+    assert dev.lib.mvb_alpha_composite(t.data_ptr(), 8, 8, 32, t.data_ptr(), 8, 8, 32, 0, 0, 2.0, 0, 0, 0, dev.stream()) == -1

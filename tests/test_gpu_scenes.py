@@ -1,0 +1,166 @@
+"""Whole-frame parity of the fused CUDA path.
+
+  * against frames rendered by the reference (tests/golden/scene_frames.npz + manifest digests) on
+    scaled-down versions of BASELINE.json's configs and on fuzz scenes (every blend mode,
+    overhanging layers, anisotropic scale, draft levels 1/2/4, both background alphas);
+  * against the CPU oracle at BASELINE.json's FULL sizes (4K / 16 layers, nested effects,
+    chroma key with draft levels), where the reference needs ~13 s per frame;
+  * size-independent properties: batched == per-frame, stack chunking, cache reuse.
+Bar: bit-exact (max |diff| = 0); the north-star tolerance is +-1 LSB.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+from scene_zoo import golden_shots
+
+pytestmark = pytest.mark.gpu
+
+
+def _mv():
+    import movis_b200 as mv
+    from movis_b200.contrib.segmentation import ChromaKey
+    return mv, ChromaKey
+
+
+def test_scene_frames_match_reference_golden(golden):
+    mv, ChromaKey = _mv()
+    g = golden("scene_frames")
+    with open(os.path.join(GOLDEN_DIR, "manifest.json")) as fh:
+        digests = json.load(fh)["digests"]
+    for tag, comp, times, bg, levels, stored in golden_shots(mv, ChromaKey):
+        for L in levels:
+            for t in times:
+                key = f"{tag}_L{L}_t{t:.3f}"
+                with comp.preview(level=L):
+                    got = comp(t, bg_color=bg)
+                if stored:
+                    d = np.abs(got.astype(np.int16) - g[key].astype(np.int16))
+                    assert d.max() == 0, f"{key}: max |diff| {d.max()}, {int((d > 0).sum())} values differ"
+                assert hashlib.sha256(got.tobytes()).hexdigest() == digests[key], key
+
+
+def _assert_matches_oracle(comp, t, bg, level=1):
+    from oracle import scene_eval
+    with comp.preview(level=level):
+        got = comp(t, bg_color=bg)
+    want = scene_eval.render(comp, t, bg, preview_level=level)
+    assert got.shape == want.shape
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert d.max() == 0, f"t={t} L={level}: max |diff| {d.max()}, {int((d > 0).sum())} values differ"
+    return got
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+def test_s2_full_size_4k_16_layers_vs_oracle(variant):
+    """BASELINE.json configs[1] at full size: 3840x2160, 16 x 1080p layers, all 18 modes over the
+    two variants, animated opacity."""
+    from movis_b200 import scenes
+    mv, _ = _mv()
+    comp = scenes.build_s2(mv, div=1, variant=variant)
+    frame = _assert_matches_oracle(comp, 2.1, (0, 0, 0, 255))
+    assert frame.shape == (2160, 3840, 4) and (frame[..., 3] == 255).all()
+    if variant == 0:
+        _assert_matches_oracle(comp, 4.9, (0, 0, 0, 0))       # transparent background: general over path
+        _assert_matches_oracle(comp, 0.3, (0, 0, 0, 255), level=2)
+
+
+def test_s1_full_size_vs_oracle():
+    from movis_b200 import scenes
+    mv, _ = _mv()
+    comp = scenes.build_s1(mv, div=1)
+    for t in (0.0, 2.5, 4.9):
+        _assert_matches_oracle(comp, t, (0, 0, 0, 255))
+
+
+def test_s3_nested_effects_full_size_vs_oracle():
+    from movis_b200 import scenes
+    mv, _ = _mv()
+    comp = scenes.build_s3(mv, div=1)
+    _assert_matches_oracle(comp, 1.7, (0, 0, 0, 255))
+
+
+def test_s4_chroma_key_draft_levels_full_size_vs_oracle():
+    from movis_b200 import scenes
+    mv, ChromaKey = _mv()
+    comp = scenes.build_s4(mv, ChromaKey, div=1, n_seq=2)
+    for level in (1, 2, 4):
+        f = _assert_matches_oracle(comp, 0.04, (0, 0, 0, 255), level=level)
+        assert f.shape == (2160 // level, 3840 // level, 4)
+
+
+def test_batched_frames_equal_per_frame_renders():
+    import torch
+    from movis_b200 import scenes
+    mv, ChromaKey = _mv()
+    for comp in (scenes.build_s2(mv, div=8), scenes.build_fuzz(mv, 3), scenes.build_s4(mv, ChromaKey, div=12),
+                 scenes.build_s3(mv, div=6)):
+        times = np.arange(0, min(comp.duration, 2.0), 1 / 30)[::3]
+        batch = comp.render_frames(times, bg_color=(3, 2, 1, 255))
+        torch.cuda.synchronize()
+        for i, t in enumerate(times):
+            assert np.array_equal(batch[i].cpu().numpy(), comp(float(t), bg_color=(3, 2, 1, 255))), (i, t)
+
+
+def test_more_layers_than_one_launch():
+    """40 layers: the stack is split across launches that continue from the stored frame."""
+    from movis_b200 import scenes
+    from movis_b200 import _native
+    mv, _ = _mv()
+    assert _native.lib().mvb_max_layers_per_launch() < 40
+    comp = scenes.build_fuzz(mv, seed=11, size=(200, 120), n_layers=40)
+    _assert_matches_oracle(comp, 0.4, (0, 0, 0, 0))
+    _assert_matches_oracle(comp, 1.1, (7, 7, 7, 255), level=2)
+
+
+def test_stream_frames_delivers_ordered_host_frames():
+    from movis_b200 import scenes
+    from movis_b200.render import stream_frames
+    mv, _ = _mv()
+    comp = scenes.build_s1(mv, div=8)
+    times = np.arange(0, 5, 1 / 30)[:21]
+    got = list(stream_frames(comp, times, bg_color=(0, 0, 0, 255), batch=4))
+    assert len(got) == 21
+    for t, f in zip(times, got):
+        assert np.array_equal(f, comp(float(t), bg_color=(0, 0, 0, 255)))
+
+    class Writer:
+        def __init__(self):
+            self.frames, self.closed = [], False
+
+        def append_data(self, f):
+            self.frames.append(f.copy())
+
+        def close(self):
+            self.closed = True
+    w = Writer()
+    comp._write_video(0.0, 0.5, 30.0, w)   # the reference's frame loop signature (composition.py:405)
+    assert w.closed and len(w.frames) == 15 and np.array_equal(w.frames[3], got[3])
+
+
+def test_render_cache_is_device_resident_and_keyed_like_the_reference():
+    import torch
+    from movis_b200 import scenes
+    mv, _ = _mv()
+    comp = scenes.build_s1(mv, div=8)
+    a = comp.render_device(1.0, (0, 0, 0, 255))
+    assert a.is_cuda and comp.render_device(1.0, (0, 0, 0, 255)) is a          # whole-frame hit
+    assert comp.render_device(1.0, (0, 0, 0, 0)) is not a                       # bg colour is part of the key
+    layer_keys = [k for k in comp.cache._entries if isinstance(k, tuple) and k[0] == mv.enum.CacheType.LAYER]
+    assert len(layer_keys) == 9                                                 # one entry per static source
+    comp.render_device(2.0, (0, 0, 0, 255))
+    assert len([k for k in comp.cache._entries if k[0] == mv.enum.CacheType.LAYER]) == 9  # animated transform: still 9
+    with comp.preview(level=2):
+        b = comp.render_device(1.0, (0, 0, 0, 255))
+    assert tuple(b.shape) == (67, 120, 4)
+    comp.add_layer(mv.layer.Image.from_color((4, 4), "red"))
+    assert len(comp.cache) == 0                                                 # add_layer clears (composition.py:319)
+    small = mv.layer.Composition(size=(64, 64), duration=1.0, cache_size_limit=3 * 64 * 64 * 4)
+    small.add_layer(lambda t: np.full((8, 8, 4), int(t * 100), np.uint8))      # no get_key: never cached as a layer
+    for i in range(6):
+        small.render_device(i / 10)
+    assert len(small.cache) <= 3 and small.cache.nbytes <= small.cache.size_limit

@@ -1,0 +1,153 @@
+"""The CPU oracle (oracle/mvo.c) against golden vectors produced by the reference itself.
+
+This is what pins the oracle: every array in tests/golden/ is an output of the unmodified
+reference (numpy / cv2 / PIL) recorded by oracle/gen_golden.py.  Bar: bit-exact everywhere.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import scene_eval
+
+from conftest import GOLDEN_DIR
+from scene_zoo import golden_shots
+
+
+def test_blend_luts_all_18_modes(golden):
+    luts = golden("blend_luts")["luts"]
+    assert luts.shape == (18, 256, 256)
+    for mode in range(18):
+        assert np.array_equal(O.blend_lut(mode), luts[mode]), O.BLEND_MODES[mode]
+    # the known answers called out in SURVEY.md 8(c)
+    sl = O.blend_lut("soft_light")
+    assert sl[32, 128] == 243 and sl[200, 255] == 225
+    assert (O.blend_lut("vivid_light")[:, 128:] == 0).all()
+
+
+def test_alpha_composite_cases(golden):
+    g = golden("alpha_composite")
+    meta = g["meta"]
+    for i, (px, py, mode, matte) in enumerate(meta):
+        out = O.alpha_composite(g[f"bg{i}"], g[f"fg{i}"], (int(px), int(py)), float(g[f"op{i}"]), int(mode), int(matte))
+        assert np.array_equal(out, g[f"out{i}"]), f"case {i}: mode {mode} matte {matte}"
+    out = O.alpha_composite(g["str_bg"], g["str_fg"], (3, 4), 0.6, "normal", use_pil=False)
+    assert np.array_equal(out, g["str_out"])
+
+
+def test_over_operators_every_alpha_pair(golden):
+    g = golden("over_alpha_pairs")
+    bg, fg = g["bg"], g["fg"]
+    assert np.array_equal(O.alpha_composite(bg, fg, (0, 0), 1.0), g["pil_1"])
+    assert np.array_equal(O.alpha_composite(bg, fg, (0, 0), 0.37), g["pil_037"])
+    assert np.array_equal(O.alpha_composite(bg, fg, (0, 0), 1.0, "soft_light"), g["soft_1"])
+    assert np.array_equal(O.alpha_composite(bg, fg, (0, 0), 0.37, "multiply"), g["mult_037"])
+
+
+def test_warp_affine(golden):
+    g = golden("warp_affine")
+    for i, (M, dsize) in enumerate(zip(g["M"], g["dsize"])):
+        out = O.warp_affine(g[f"src{i}"], M.reshape(2, 3), (int(dsize[0]), int(dsize[1])))
+        assert np.array_equal(out, g[f"dst{i}"]), f"case {i}"
+
+
+def test_gaussian_weights_known_answers():
+    # Q0.8 kernels OpenCV generates
+    assert O.gaussian_weights_q8(0.5, 3).tolist() == [27, 202, 27]
+    assert O.gaussian_weights_q8(1.0, 5).tolist() == [14, 62, 104, 62, 14]
+    w10 = O.gaussian_weights_q8(10.0, 41)
+    assert w10.sum() == 256 and w10[20] == 10 and w10[:6].tolist() == [1, 2, 2, 3, 3, 3]
+    w25 = O.gaussian_weights_q8(25.0, 101)
+    assert w25.sum() == 256 and (w25 == 0).any()
+    assert O.blur_ksize(10) == 41 and O.blur_ksize(3) == 13 and O.blur_ksize(0.1) == 3
+
+
+def test_gaussian_blur(golden):
+    g = golden("gaussian_blur")
+    for i, r in enumerate(g["radii"]):
+        k = O.blur_ksize(float(r))
+        assert np.array_equal(O.gaussian_blur_u8(g[f"src4_{i}"], k, float(r)), g[f"dst4_{i}"]), f"radius {r} rgba"
+        assert np.array_equal(O.gaussian_blur_u8(g[f"src1_{i}"], k, float(r)), g[f"dst1_{i}"]), f"radius {r} gray"
+
+
+def test_effects(golden):
+    g = golden("effects")
+    for i, p in enumerate(g["params"]):
+        r, st, off, ang, op = (float(v) for v in p[:5])
+        col = tuple(int(v) for v in p[5:8])
+        hu, sat, lum = (float(v) for v in p[8:11])
+        krange = tuple(float(v) for v in p[11:14])
+        img = g[f"img{i}"]
+        assert np.array_equal(O.effect_gaussian_blur(img, r), g[f"blur{i}"]), f"blur {i}"
+        assert np.array_equal(O.effect_glow(img, r, st), g[f"glow{i}"]), f"glow {i}"
+        assert np.array_equal(O.effect_drop_shadow(img, r, off, ang, col, op), g[f"shadow{i}"]), f"shadow {i}"
+        assert np.array_equal(O.effect_fill_color(img, col), g[f"fill{i}"]), f"fill {i}"
+        assert np.array_equal(O.effect_hsl_shift(img, hu, sat, lum), g[f"hsl{i}"]), f"hsl {i}"
+        assert np.array_equal(O.effect_chroma_key(g[f"keyed{i}"], col, krange), g[f"chroma{i}"]), f"chroma {i}"
+    lo, hi = O.chroma_key_bounds()
+    assert np.array_equal(np.stack([lo, hi]), g["chroma_default_bounds"])
+    assert lo.tolist() == [50, 178, 178] and hi.tolist() == [70, 255, 255]
+
+
+def test_colour_conversions(golden):
+    g = golden("color_convert")
+    assert np.array_equal(O.rgb2hsv(g["rgb"]), g["hsv"])
+    assert np.array_equal(O.hsv2rgb(g["hsv_in"]), g["rgb_out"])  # includes cv2's row-tail rounding
+
+
+def test_affine_geometry(golden):
+    g = golden("host_engine")
+    names = {1: "bottom_left", 2: "bottom_center", 3: "bottom_right", 4: "center_left", 5: "center",
+             6: "center_right", 7: "top_left", 8: "top_center", 9: "top_right"}
+    for row, want in zip(g["transform_inputs"], g["affine_plans"]):
+        w, h = int(row[0]), int(row[1])
+        p = O.TransformSample(anchor_point=(row[2], row[3]), position=(row[4], row[5]), scale=(row[6], row[7]),
+                              rotation=row[8], origin_point=names[int(row[9])])
+        r = O.fixed_affine(p, (w, h), int(row[10]))
+        if want[10] == 0:
+            assert r is None
+        else:
+            A, (W, H), (ox, oy) = r
+            assert np.array_equal(A.reshape(6), want[:6])
+            assert [ox, oy, W, H] == [int(v) for v in want[6:10]]
+
+
+def test_division_shortcuts_are_exact():
+    """The two division shortcuts the CUDA kernels rely on, checked exhaustively on the CPU:
+    x // 255 == (x * 0x8081) >> 23 for x < 65536, and the float-reciprocal quotient estimate is
+    within +-1 of floor(n / d) for every (oa, quotient boundary) pair of the numpy 'over'."""
+    x = np.arange(65536, dtype=np.uint64)
+    assert np.array_equal(x // 255, (x * 0x8081) >> 23)
+    d = np.arange(255, 65026, dtype=np.int64)
+    rd = (np.float32(1.0) / d.astype(np.float32))
+    for q in (1, 2, 127, 128, 254, 255):
+        for delta in (-1, 0, 1):
+            n = q * d + delta
+            n = n[(n >= 0) & (n < (1 << 24))]
+            dd = d[: len(n)]
+            est = np.floor(n.astype(np.float32) * rd[: len(n)]).astype(np.int64)
+            assert np.abs(est - n // dd).max() <= 1
+
+
+def test_scene_walker_matches_reference_frames(golden):
+    """Whole Composition.__call__ renders: oracle scene walker over movis_b200's scene objects
+    (host keyframe engine) against frames rendered by the reference."""
+    import movis_b200 as mv
+    from movis_b200.contrib.segmentation import ChromaKey
+    g = golden("scene_frames")
+    with open(os.path.join(GOLDEN_DIR, "manifest.json")) as fh:
+        digests = json.load(fh)["digests"]
+    n = 0
+    for tag, comp, times, bg, levels, stored in golden_shots(mv, ChromaKey):
+        for L in levels:
+            for t in times:
+                key = f"{tag}_L{L}_t{t:.3f}"
+                got = scene_eval.render(comp, t, bg, preview_level=L)
+                assert hashlib.sha256(got.tobytes()).hexdigest() == digests[key], key
+                if stored:
+                    assert np.array_equal(got, g[key]), key
+                n += 1
+    assert n == 68
