@@ -493,7 +493,7 @@ class Composition:
         1/fps)`` in batches on the GPU and hands uint8 frames to ``writer.append_data`` in order."""
         from ..render import stream_frames
         times = np.arange(start_time, end_time, 1.0 / fps)
-        for frame in stream_frames(self, times, bg_color=(0, 0, 0, 255)):
+        for frame in stream_frames(self, times, bg_color=(0, 0, 0, 255), copy=False):
             writer.append_data(frame)
         writer.close()
 

@@ -161,8 +161,13 @@ def render_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 
     return out
 
 
-def stream_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 255), batch: int = 8) -> Iterator[np.ndarray]:
+def stream_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 255), batch: int = 8,
+                  copy: bool = True) -> Iterator[np.ndarray]:
     """Yield host uint8 frames for ``times`` in order.
+
+    With ``copy=False`` the yielded arrays are views into the pinned staging buffers and stay
+    valid only until the generator is advanced ``batch`` more frames (enough for a writer that
+    consumes each frame immediately, like the reference's ``writer.append_data`` loop).
 
     Two device batches and two pinned host batches alternate: while batch i is copied to the
     host on a side stream and consumed by the caller, batch i + 1 is planned and rendered."""
@@ -197,4 +202,4 @@ def stream_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 
         copy_done[slot].synchronize()
         frames = host[slot].numpy()
         for j in range(len(chunk)):
-            yield frames[j].copy()
+            yield frames[j].copy() if copy else frames[j]
