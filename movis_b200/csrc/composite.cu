@@ -9,10 +9,11 @@
 //               cv::warpAffine's integer tables restricted to the tile (adelta/bdelta for the 32
 //               columns, X0/Y0 for the 32 rows; fp64 without FMA contraction) and a 256-entry
 //               alpha LUT that applies the layer opacity exactly like the reference path does;
-//   main loop - each thread owns one column and 8 rows; for each of its pixels it walks the
-//               surviving layers in paint order with the pixel in a register (re-quantised to
-//               4xu8 after every layer, as the reference does), gathering the 4 bilinear taps
-//               through L1 and blending with exact integer arithmetic;
+//   main loop - each thread owns one column and 8 rows of the tile (pixels parked in shared memory,
+//               re-quantised to 4xu8 after every layer, as the reference does).  Layers are the
+//               OUTER loop: per layer the thread loads the descriptor once, samples its rows
+//               (4 bilinear taps gathered through L1, cv2's fixed-point weights) into shared
+//               memory, then jumps once to the blend loop specialised for the layer's mode;
 //   epilogue  - one coalesced 128-byte store per warp row.  The frame is written exactly once.
 #include <cmath>
 #include <cstdio>
@@ -29,6 +30,7 @@ constexpr int kTileW = 32;
 constexpr int kTileH = 32;
 constexpr int kWarps = 4;
 constexpr int kMaxLayers = 32; // per launch; 32 * 104 B of descriptors stay under the 4 KB param limit
+constexpr int kSlots = 16;     // layers whose per-tile tables are resident in shared memory at a time
 
 struct DevLayer {
     const uint8_t* src;
@@ -53,91 +55,178 @@ struct StackParams {
     DevLayer layers[kMaxLayers];
 };
 
+// Phase 2 of one layer: blend the samples parked in shared memory into the thread's pixels.  The
+// blend mode is a template parameter, so this loop has no per-pixel dispatch; it is the only code
+// that exists once per mode (MODE == kPilOver selects PIL's arithmetic).
+constexpr int kPilOver = 18;
+
+template <int MODE>
+__device__ __forceinline__ void blend_rows(const uint32_t* __restrict__ smpcol, uint32_t* __restrict__ pxcol,
+                                        int r0, int r1)
+{
+#pragma unroll 1
+    for (int row = r0; row < r1; ++row) {
+        const uint32_t sp = smpcol[row * kTileW]; // r, g, b, opacity-scaled alpha
+        const uint32_t px = pxcol[row * kTileW];
+        const uint32_t fa = sp >> 24;
+        uint32_t out;
+        if constexpr (MODE == kPilOver) {
+            if (fa == 0) continue;
+            out = over_pil(px, unpack(sp), fa);
+        } else {
+            // transparent sample: no-op unless bg alpha is 0, where numpy zeroes rgb (imgproc.py:164)
+            if (fa == 0) out = (px >> 24) == 0 ? 0u : px;
+            else out = over_numpy<MODE>(px, unpack(sp), fa, false);
+        }
+        pxcol[row * kTileW] = out;
+    }
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
 k_composite_stack(const __grid_constant__ StackParams P)
 {
-    __shared__ int2 s_col[kMaxLayers][kTileW];     // (adelta, bdelta) per tile column
-    __shared__ int2 s_row[kMaxLayers][kTileH];     // (X0, Y0) per tile row
-    __shared__ uint8_t s_lut[kMaxLayers][256];     // opacity-scaled alpha
+    __shared__ int2 s_col[kSlots][kTileW];         // (adelta, bdelta) per tile column
+    __shared__ int2 s_row[kSlots][kTileH];         // (X0, Y0) per tile row
+    __shared__ uint8_t s_lut[kSlots][256];         // opacity-scaled alpha
+    __shared__ uint32_t s_px[kTileH][kTileW];      // the tile's pixels while the stack is walked
+    __shared__ uint32_t s_smp[kTileH][kTileW];     // the current layer's samples
     __shared__ int s_active[kMaxLayers];
+    __shared__ int s_empty[kMaxLayers];            // 1: no tap of this tile falls inside the source
     __shared__ int s_nactive;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
 
-    // ---- prologue: cull + tables -----------------------------------------------------------
+    // ---- cull + classify the layers against this tile -------------------------------------------
     if (warp == 0) {
-        bool hit = false;
+        bool hit = false, empty = false;
         if (lane < P.n_layers) {
             const DevLayer& L = P.layers[lane];
-            hit = L.bw > 0 && L.bh > 0 && tx0 < L.bx + L.bw && tx0 + kTileW > L.bx &&
-                  ty0 < L.by + L.bh && ty0 + kTileH > L.by;
+            // tile ∩ bbox ∩ frame, in bbox coordinates (inclusive corners)
+            const int u0 = max(tx0, L.bx) - L.bx, u1 = min(min(tx0 + kTileW, L.bx + L.bw), P.W) - 1 - L.bx;
+            const int v0 = max(ty0, L.by) - L.by, v1 = min(min(ty0 + kTileH, L.by + L.bh), P.H) - 1 - L.by;
+            hit = L.bw > 0 && L.bh > 0 && u0 <= u1 && v0 <= v1;
+            if (hit) {
+                // source-space extent of that rectangle (affine: extrema at the corners); 0.25 px of
+                // slack covers the 1/32 px coordinate quantisation
+                double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double u = (k & 1) ? u1 : u0, v = (k & 2) ? v1 : v0;
+                    const double xs = L.m[0] * u + L.m[1] * v + L.m[2];
+                    const double ys = L.m[3] * u + L.m[4] * v + L.m[5];
+                    xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
+                    ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
+                }
+                empty = xmax < -1.25 || xmin > L.src_w + 0.25 || ymax < -1.25 || ymin > L.src_h + 0.25;
+                // an empty tile of a PIL-path layer is a no-op: drop it altogether
+                if (empty && L.pil) hit = false;
+            }
         }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) s_active[__popc(m & ((1u << lane) - 1u))] = lane;
+        if (hit) {
+            const int slot = __popc(m & ((1u << lane) - 1u));
+            s_active[slot] = lane;
+            s_empty[slot] = empty ? 1 : 0;
+        }
         if (lane == 0) s_nactive = __popc(m);
+    }
+
+    // ---- the thread's pixels: column `lane`, rows [8 warp, 8 warp + 8) -------------------------
+    const int x = tx0 + lane;
+    const int rbeg = warp * (kTileH / kWarps);
+    const int rend = min(rbeg + kTileH / kWarps, P.H - ty0);
+    const bool x_ok = x < P.W;
+    uint32_t* const pxcol = &s_px[0][lane];
+    uint32_t* const smpcol = &s_smp[0][lane];
+    if (x_ok) {
+        for (int row = rbeg; row < rend; ++row) {
+            uint32_t v = P.bg;
+            if (P.keep_frame) v = reinterpret_cast<const uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x];
+            pxcol[row * kTileW] = v;
+        }
     }
     __syncthreads();
     const int n_active = s_nactive;
 
-    for (int i = tid; i < n_active * (kTileW + kTileH); i += kWarps * 32) {
-        const int slot = i / (kTileW + kTileH), j = i % (kTileW + kTileH);
-        const DevLayer& L = P.layers[s_active[slot]];
-        if (j < kTileW) {
-            const int u = tx0 + j - L.bx;
-            s_col[slot][j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
-        } else {
-            const int v = ty0 + (j - kTileW) - L.by;
-            s_row[slot][j - kTileW] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
-        }
-    }
-    for (int i = tid; i < n_active * 256; i += kWarps * 32) {
-        const int slot = i >> 8, a = i & 255;
-        const DevLayer& L = P.layers[s_active[slot]];
-        uint32_t v = (uint32_t)a;
-        if (L.opacity < 1.0) {
-            v = L.pil ? (uint32_t)(a * L.pil_a) / 255u                      // imgproc.py:206-208
-                      : __double2uint_rz(__dmul_rn((double)a, L.opacity));  // imgproc.py:159
-        }
-        s_lut[slot][a] = (uint8_t)v;
-    }
-    __syncthreads();
-
-    // ---- main loop -------------------------------------------------------------------------
-    const int x = tx0 + lane;
-    if (x >= P.W) return;
-#pragma unroll 1
-    for (int rr = 0; rr < kTileH / kWarps; ++rr) {
-        const int row = rr * kWarps + warp;
-        const int y = ty0 + row;
-        if (y >= P.H) break;
-        uint32_t* out = reinterpret_cast<uint32_t*>(P.frame + (int64_t)y * P.stride) + x;
-        uint32_t px = P.keep_frame ? *out : P.bg;
-#pragma unroll 1
-        for (int slot = 0; slot < n_active; ++slot) {
-            const DevLayer& L = P.layers[s_active[slot]];
-            const int u = x - L.bx, v = y - L.by;
-            if ((unsigned)v >= (unsigned)L.bh || (unsigned)u >= (unsigned)L.bw) continue;
-            const int2 c = s_col[slot][lane];
-            const int2 r = s_row[slot][row];
-            const int X = (r.x + c.x) >> 5, Y = (r.y + c.y) >> 5;
-            Rgba s;
-            uint32_t fa = 0;
-            if (sample_q5(L.src, L.src_w, L.src_h, L.src_stride, X, Y, s)) fa = s_lut[slot][s.a];
-            else s = Rgba{0, 0, 0, 0};
-            if (L.pil) {
-                px = over_pil(px, s, fa);
-            } else if (fa == 0) {
-                // numpy path with a transparent sample: no-op unless bg alpha is 0, where the
-                // reference zeroes rgb (imgproc.py:164 with out_a == 0)
-                if ((px >> 24) == 0) px = 0;
+    // ---- walk the stack in paint order, kSlots layers' tables at a time --------------------------
+    for (int base = 0; base < n_active; base += kSlots) {
+        const int n_here = min(kSlots, n_active - base);
+        if (base > 0) __syncthreads(); // everyone is done with the previous tables
+        for (int i = tid; i < n_here * (kTileW + kTileH); i += kWarps * 32) {
+            const int slot = i / (kTileW + kTileH), j = i % (kTileW + kTileH);
+            if (s_empty[base + slot]) continue;
+            const DevLayer& L = P.layers[s_active[base + slot]];
+            if (j < kTileW) {
+                const int u = tx0 + j - L.bx;
+                s_col[slot][j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
             } else {
-                px = over_numpy_dyn(L.mode, px, s, fa, false);
+                const int v = ty0 + (j - kTileW) - L.by;
+                s_row[slot][j - kTileW] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
             }
         }
-        *out = px;
+        for (int i = tid; i < n_here * 256; i += kWarps * 32) {
+            const int slot = i >> 8, a = i & 255;
+            if (s_empty[base + slot]) continue;
+            const DevLayer& L = P.layers[s_active[base + slot]];
+            uint32_t v = (uint32_t)a;
+            if (L.opacity < 1.0) {
+                v = L.pil ? (uint32_t)(a * L.pil_a) / 255u                      // imgproc.py:206-208
+                          : __double2uint_rz(__dmul_rn((double)a, L.opacity));  // imgproc.py:159
+            }
+            s_lut[slot][a] = (uint8_t)v;
+        }
+        __syncthreads();
+        if (!x_ok) continue;
+
+#pragma unroll 1
+        for (int slot = 0; slot < n_here; ++slot) {
+            const DevLayer& L = P.layers[s_active[base + slot]];
+            const int u = x - L.bx;
+            if ((unsigned)u >= (unsigned)L.bw) continue;
+            const int r0 = max(rbeg, L.by - ty0), r1 = min(rend, L.by + L.bh - ty0);
+            if (r0 >= r1) continue;
+            if (s_empty[base + slot]) { // numpy path, every sample transparent
+                for (int row = r0; row < r1; ++row) {
+                    const uint32_t px = pxcol[row * kTileW];
+                    if ((px >> 24) == 0 && px != 0) pxcol[row * kTileW] = 0;
+                }
+                continue;
+            }
+            // phase 1: sample the layer at the thread's pixels (mode-independent code)
+            {
+                const uint8_t* __restrict__ src = L.src;
+                const int sw = L.src_w, sh = L.src_h, ss = L.src_stride;
+                const int2 col = s_col[slot][lane];
+                const int2* __restrict__ rowtab = s_row[slot];
+                const uint8_t* __restrict__ lut = s_lut[slot];
+#pragma unroll 2
+                for (int row = r0; row < r1; ++row) {
+                    const int2 r = rowtab[row];
+                    const int X = (r.x + col.x) >> 5, Y = (r.y + col.y) >> 5;
+                    Rgba s;
+                    uint32_t sp = 0;
+                    if (sample_q5(src, sw, sh, ss, X, Y, s)) sp = pack(s.r, s.g, s.b, lut[s.a]);
+                    smpcol[row * kTileW] = sp;
+                }
+            }
+            // phase 2: blend, in the loop specialised for this layer's mode
+            switch (L.pil ? kPilOver : L.mode) {
+#define MVB_ROWS(M) case M: blend_rows<M>(smpcol, pxcol, r0, r1); break;
+                MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
+                MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
+                MVB_ROWS(15) MVB_ROWS(16) MVB_ROWS(17) MVB_ROWS(18)
+#undef MVB_ROWS
+            default: break;
+            }
+        }
     }
+
+    // ---- epilogue: one coalesced 128-byte store per warp row -----------------------------------
+    if (x_ok)
+        for (int row = rbeg; row < rend; ++row)
+            reinterpret_cast<uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x] = pxcol[row * kTileW];
 }
 
 // cv2.warpAffine stand-alone: one thread per destination pixel.
@@ -225,6 +314,8 @@ static int fill_dev_layer(const mvb_layer& in, DevLayer& out)
     if (in.src_stride < (int64_t)in.src_w * 4 || (in.src_stride & 3) || in.src_stride > 0x7FFFFFFF ||
         (reinterpret_cast<uintptr_t>(in.src) & 3))
         return set_error(MVB_ERR_INVALID_ARG, "layer source stride/pointer must be 4-byte aligned and >= 4*width");
+    if ((int64_t)in.src_h * in.src_stride > 0xFFFFFFFFll)
+        return set_error(MVB_ERR_UNSUPPORTED, "layer source must span less than 4 GiB");
     if (in.blend_mode < 0 || in.blend_mode >= MVB_BLEND_COUNT)
         return set_error(MVB_ERR_INVALID_ARG, "unknown blend mode");
     if (!(in.opacity >= 0.0 && in.opacity <= 1.0))
@@ -324,7 +415,8 @@ extern "C" int mvb_warp_affine_rgba8(const void* src, int32_t sw, int32_t sh, in
     if (int rc = require_device()) return rc;
     if (int rc = check_image(src, sw, sh, sstride, "src")) return rc;
     if (int rc = check_image(dst, dw, dh, dstride, "dst")) return rc;
-    if (!M || sw >= 32768 || sh >= 32768) return set_error(MVB_ERR_INVALID_ARG, "bad matrix or source too large");
+    if (!M || sw >= 32768 || sh >= 32768 || (int64_t)sh * sstride > 0xFFFFFFFFll)
+        return set_error(MVB_ERR_INVALID_ARG, "bad matrix or source too large");
     double m[6];
     invert_affine_cv(M, m);
     const dim3 grid((dw + 31) / 32, (dh + 7) / 8);

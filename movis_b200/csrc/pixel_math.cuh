@@ -216,14 +216,15 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p)
 
 // Sample `src` at fixed-point (X, Y) with 5 fractional bits; taps outside the image read 0
 // (BORDER_CONSTANT).  Returns false when all four taps are outside (sample is transparent black).
+// Byte offsets are 32-bit: a source image is < 2 GiB (checked on the host).
 __device__ __forceinline__ bool sample_q5(const uint8_t* __restrict__ src, int sw, int sh, int stride,
                                           int X, int Y, Rgba& out)
 {
     const int sx = X >> 5, sy = Y >> 5;
     const uint32_t fx = X & 31, fy = Y & 31;
-    const uint8_t* base = src + (int64_t)sy * stride + (int64_t)sx * 4;
     uint32_t p00, p01, p10, p11;
     if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+        const uint8_t* base = src + ((uint32_t)sy * (uint32_t)stride + (uint32_t)sx * 4u);
         p00 = ldg_u32(base);
         p01 = ldg_u32(base + 4);
         p10 = ldg_u32(base + stride);
@@ -232,13 +233,13 @@ __device__ __forceinline__ bool sample_q5(const uint8_t* __restrict__ src, int s
         const bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
         const bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;
         if (!((x0 | x1) & (y0 | y1))) return false;
+        const uint8_t* base = src + (int64_t)sy * stride + (int64_t)sx * 4;
         p00 = (x0 & y0) ? ldg_u32(base) : 0u;
         p01 = (x1 & y0) ? ldg_u32(base + 4) : 0u;
         p10 = (x0 & y1) ? ldg_u32(base + stride) : 0u;
         p11 = (x1 & y1) ? ldg_u32(base + stride + 4) : 0u;
     }
-    if ((fx | fy) == 0) { out = unpack(p00); return true; }
-    out = bilinear_q5(p00, p01, p10, p11, fx, fy);
+    out = bilinear_q5(p00, p01, p10, p11, fx, fy); // fx == fy == 0 reproduces p00 exactly
     return true;
 }
 
