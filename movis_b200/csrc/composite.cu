@@ -53,194 +53,238 @@ struct StackParams {
     uint32_t bg;
     int32_t n_layers;
     int32_t keep_frame;
+    int32_t needs_tables; // some layer uses color_dodge / color_burn / soft_light / vivid_light
+    int32_t pad_;
     DevLayer layers[kMaxLayers];
 };
 
 constexpr int kPilOver = 18; // dispatch code of PIL's "over" next to the 18 numpy blend modes
 
-// The rare path: background alpha != 255 (transparent / translucent frame).  Out of line and with
-// dynamic mode dispatch so that the hot loop only carries the division-free arithmetic.
-__device__ __noinline__ uint32_t over_general(int code, uint32_t px, uint32_t sp)
+// Host-initialised tables for the division / sqrt heavy blend modes (see BlendTables).
+struct BlendTableData { uint32_t rcp24[260]; uint32_t softg[256]; };
+__device__ BlendTableData g_blend_tables;
+
+// Phase 2 of one layer: blend the samples parked in shared memory into the thread's pixels.
+// MODE is a template parameter (18 numpy modes + PIL "over"), so the loop has no per-pixel
+// dispatch.  OPAQUE: the frame's alpha is 255 everywhere (opaque bg_color), which both "over"
+// operators preserve -- the division-free arithmetic is then the only code that exists.
+template <int MODE, bool OPAQUE>
+__device__ __forceinline__ void blend_rows(const uint32_t* __restrict__ smpcol, uint32_t* __restrict__ pxcol,
+                                           int r0, int r1, const BlendTables& tabs)
 {
-    const Rgba s = unpack(sp);
-    if (code == kPilOver) return over_pil(px, s, s.a);
-    return over_numpy_dyn(code, px, s, s.a, false);
+#pragma unroll 1
+    for (int row = r0; row < r1; ++row) {
+        const uint32_t sp = smpcol[row * kTileW]; // r, g, b, opacity-scaled alpha
+        const uint32_t px = pxcol[row * kTileW];
+        const uint32_t fa = sp >> 24;
+        uint32_t out;
+        if (fa == 0) {
+            // PIL: no-op.  numpy: no-op unless bg alpha is 0, where rgb is zeroed (imgproc.py:164)
+            if (OPAQUE || MODE == kPilOver || px >= 0x01000000u) continue;
+            out = 0;
+        } else if (OPAQUE || px >= 0xFF000000u) {
+            const uint32_t sr = sp & 0xFFu, sg = __byte_perm(sp, 0, 0x4441), sb = __byte_perm(sp, 0, 0x4442);
+            const uint32_t dr = px & 0xFFu, dg = __byte_perm(px, 0, 0x4441), db = __byte_perm(px, 0, 0x4442);
+            const uint32_t ia = 255 - fa;
+            uint32_t r, g, b;
+            if constexpr (MODE == kPilOver) {
+                const uint32_t tr = 128 * (sr * fa + dr * ia) + 0x4000;
+                const uint32_t tg = 128 * (sg * fa + dg * ia) + 0x4000;
+                const uint32_t tb = 128 * (sb * fa + db * ia) + 0x4000;
+                r = (((tr >> 8) + tr) >> 8) >> 7;
+                g = (((tg >> 8) + tg) >> 8) >> 7;
+                b = (((tb >> 8) + tb) >> 8) >> 7;
+            } else {
+                r = div255(fa * blend_target_tab<MODE>(dr, sr, tabs) + ia * dr);
+                g = div255(fa * blend_target_tab<MODE>(dg, sg, tabs) + ia * dg);
+                b = div255(fa * blend_target_tab<MODE>(db, sb, tabs) + ia * db);
+            }
+            out = r | (g << 8) | (b << 16) | 0xFF000000u;
+        } else if constexpr (MODE == kPilOver) {
+            out = over_pil(px, unpack(sp), fa);
+        } else {
+            out = over_numpy<MODE>(px, unpack(sp), fa, false);
+        }
+        pxcol[row * kTileW] = out;
+    }
 }
 
-// Opaque-background blend of one pixel (bg alpha 255 stays 255): no division.
-template <int MODE>
-__device__ __forceinline__ uint32_t blend_opaque(uint32_t px, const Rgba& s, uint32_t fa)
-{
-    const uint32_t dr = px & 0xFFu, dg = __byte_perm(px, 0, 0x4441), db = __byte_perm(px, 0, 0x4442);
-    const uint32_t ia = 255 - fa;
-    uint32_t r, g, b;
-    if constexpr (MODE == kPilOver) {
-        const uint32_t tr = 128 * (s.r * fa + dr * ia) + 0x4000;
-        const uint32_t tg = 128 * (s.g * fa + dg * ia) + 0x4000;
-        const uint32_t tb = 128 * (s.b * fa + db * ia) + 0x4000;
-        r = (((tr >> 8) + tr) >> 8) >> 7;
-        g = (((tg >> 8) + tg) >> 8) >> 7;
-        b = (((tb >> 8) + tb) >> 8) >> 7;
-    } else {
-        r = div255(fa * blend_target<MODE>(dr, s.r) + ia * dr);
-        g = div255(fa * blend_target<MODE>(dg, s.g) + ia * dg);
-        b = div255(fa * blend_target<MODE>(db, s.b) + ia * db);
-    }
-    return r | (g << 8) | (b << 16) | 0xFF000000u;
-}
+enum { kTileEdge = 0, kTileEmpty = 1, kTileInterior = 2 };
 
 // One CTA per kTileW x kTileH output tile (thread = 1 column x kRows rows).
+template <bool OPAQUE>
 __global__ void __launch_bounds__(kWarps * 32)
 k_composite_stack(const __grid_constant__ StackParams P)
 {
-    __shared__ uint8_t s_lut[kSlots][256];         // opacity-scaled alpha
     __shared__ int2 s_col[kSlots][kTileW];         // (adelta, bdelta) per tile column
     __shared__ int2 s_row[kSlots][kTileH];         // (X0, Y0) per tile row
+    __shared__ uint8_t s_lut[kSlots][256];         // opacity-scaled alpha
     __shared__ uint32_t s_px[kTileH][kTileW];      // the tile's pixels while the stack is walked
+    __shared__ uint32_t s_smp[kTileH][kTileW];     // the current layer's samples
+    __shared__ uint32_t s_rcp24[260];
+    __shared__ uint32_t s_softg[256];
     __shared__ int s_active[kMaxLayers];
-    __shared__ int s_empty[kMaxLayers];            // 1: no tap of this tile falls inside the source
+    __shared__ int s_class[kMaxLayers];
     __shared__ int s_nactive;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
 
-    {
-        const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
-
-        // ---- cull + classify the layers against this tile ---------------------------------------
-        if (warp == 0) {
-            bool hit = false, empty = false;
-            if (lane < P.n_layers) {
-                const DevLayer& L = P.layers[lane];
-                // tile ∩ bbox ∩ frame, in bbox coordinates (inclusive corners)
-                const int u0 = max(tx0, L.bx) - L.bx, u1 = min(min(tx0 + kTileW, L.bx + L.bw), P.W) - 1 - L.bx;
-                const int v0 = max(ty0, L.by) - L.by, v1 = min(min(ty0 + kTileH, L.by + L.bh), P.H) - 1 - L.by;
-                hit = L.bw > 0 && L.bh > 0 && u0 <= u1 && v0 <= v1;
-                if (hit) {
-                    // source-space extent of that rectangle (affine: extrema at the corners); 0.25 px
-                    // of slack covers the 1/32 px coordinate quantisation
-                    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const double u = (k & 1) ? u1 : u0, v = (k & 2) ? v1 : v0;
-                        const double xs = L.m[0] * u + L.m[1] * v + L.m[2];
-                        const double ys = L.m[3] * u + L.m[4] * v + L.m[5];
-                        xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
-                        ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
-                    }
-                    empty = xmax < -1.25 || xmin > L.src_w + 0.25 || ymax < -1.25 || ymin > L.src_h + 0.25;
-                    if (empty && L.pil) hit = false; // an empty tile of a PIL-path layer is a no-op
-                }
-            }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    // ---- cull + classify the layers against this tile -------------------------------------------
+    if (warp == 0) {
+        bool hit = false;
+        int cls = kTileEdge;
+        if (lane < P.n_layers) {
+            const DevLayer& L = P.layers[lane];
+            // tile ∩ bbox ∩ frame, in bbox coordinates (inclusive corners)
+            const int u0 = max(tx0, L.bx) - L.bx, u1 = min(min(tx0 + kTileW, L.bx + L.bw), P.W) - 1 - L.bx;
+            const int v0 = max(ty0, L.by) - L.by, v1 = min(min(ty0 + kTileH, L.by + L.bh), P.H) - 1 - L.by;
+            hit = L.bw > 0 && L.bh > 0 && u0 <= u1 && v0 <= v1;
             if (hit) {
-                const int slot = __popc(m & ((1u << lane) - 1u));
-                s_active[slot] = lane;
-                s_empty[slot] = empty ? 1 : 0;
+                // source-space extent of that rectangle (affine: extrema at the corners); 0.25 px of
+                // slack covers the 1/32 px coordinate quantisation and its +16/1024 rounding offset
+                double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double u = (k & 1) ? u1 : u0, v = (k & 2) ? v1 : v0;
+                    const double xs = L.m[0] * u + L.m[1] * v + L.m[2];
+                    const double ys = L.m[3] * u + L.m[4] * v + L.m[5];
+                    xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
+                    ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
+                }
+                const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == kTileH - 1;
+                if (xmax < -1.25 || xmin > L.src_w + 0.25 || ymax < -1.25 || ymin > L.src_h + 0.25)
+                    cls = kTileEmpty;      // no tap of this tile falls inside the source
+                else if (full && xmin > 0.25 && xmax < L.src_w - 1.25 && ymin > 0.25 && ymax < L.src_h - 1.25)
+                    cls = kTileInterior;   // whole tile covered and every tap inside the source
+                // an empty tile is a no-op for PIL, and for numpy too when the frame is opaque
+                if (cls == kTileEmpty && (L.pil || OPAQUE)) hit = false;
             }
-            if (lane == 0) s_nactive = __popc(m);
         }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hit) {
+            const int slot = __popc(m & ((1u << lane) - 1u));
+            s_active[slot] = lane;
+            s_class[slot] = cls;
+        }
+        if (lane == 0) s_nactive = __popc(m);
+    }
+    if (P.needs_tables) {
+        for (int i = tid; i < 260; i += kWarps * 32) s_rcp24[i] = g_blend_tables.rcp24[i];
+        for (int i = tid; i < 256; i += kWarps * 32) s_softg[i] = g_blend_tables.softg[i];
+    }
+    const BlendTables tabs{s_rcp24, s_softg};
 
-        // ---- the thread's pixels: column `lane`, rows [kRows warp, kRows warp + kRows) -----------
-        const int x = tx0 + lane;
-        const int rbeg = warp * kRows;
-        const int rend = min(rbeg + kRows, P.H - ty0);
-        const bool x_ok = x < P.W;
-        uint32_t* const pxcol = &s_px[0][lane];
-        if (x_ok) {
-            for (int row = rbeg; row < rend; ++row) {
-                uint32_t v = P.bg;
-                if (P.keep_frame) v = reinterpret_cast<const uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x];
-                pxcol[row * kTileW] = v;
+    // ---- the thread's pixels: column `lane`, rows [kRows warp, kRows warp + kRows) ---------------
+    const int x = tx0 + lane;
+    const int rbeg = warp * kRows;
+    const int rend = min(rbeg + kRows, P.H - ty0);
+    const bool x_ok = x < P.W;
+    uint32_t* const pxcol = &s_px[0][lane];
+    uint32_t* const smpcol = &s_smp[0][lane];
+    if (x_ok) {
+        for (int row = rbeg; row < rend; ++row) {
+            uint32_t v = P.bg;
+            if (P.keep_frame) v = reinterpret_cast<const uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x];
+            pxcol[row * kTileW] = v;
+        }
+    }
+    __syncthreads();
+    const int n_active = s_nactive;
+
+    // ---- walk the stack in paint order, kSlots layers' tables at a time --------------------------
+    for (int base = 0; base < n_active; base += kSlots) {
+        const int n_here = min(kSlots, n_active - base);
+        if (base > 0) __syncthreads();
+        for (int i = tid; i < n_here * (kTileW + kTileH); i += kWarps * 32) {
+            const int slot = i / (kTileW + kTileH), j = i % (kTileW + kTileH);
+            if (s_class[base + slot] == kTileEmpty) continue;
+            const DevLayer& L = P.layers[s_active[base + slot]];
+            if (j < kTileW) {
+                const int u = tx0 + j - L.bx;
+                s_col[slot][j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
+            } else {
+                const int v = ty0 + (j - kTileW) - L.by;
+                s_row[slot][j - kTileW] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
             }
+        }
+        for (int i = tid; i < n_here * 256; i += kWarps * 32) {
+            const int slot = i >> 8, a = i & 255;
+            if (s_class[base + slot] == kTileEmpty) continue;
+            const DevLayer& L = P.layers[s_active[base + slot]];
+            uint32_t v = (uint32_t)a;
+            if (L.opacity < 1.0)
+                v = L.pil ? (uint32_t)(a * L.pil_a) / 255u                      // imgproc.py:206-208
+                          : __double2uint_rz(__dmul_rn((double)a, L.opacity));  // imgproc.py:159
+            s_lut[slot][a] = (uint8_t)v;
         }
         __syncthreads();
-        const int n_active = s_nactive;
-
-        // ---- walk the stack in paint order, kSlots layers' tables at a time ------------------------
-        for (int base = 0; base < n_active; base += kSlots) {
-            const int n_here = min(kSlots, n_active - base);
-            if (base > 0) __syncthreads();
-            for (int i = tid; i < n_here * (kTileW + kTileH); i += kWarps * 32) {
-                const int slot = i / (kTileW + kTileH), j = i % (kTileW + kTileH);
-                if (s_empty[base + slot]) continue;
-                const DevLayer& L = P.layers[s_active[base + slot]];
-                if (j < kTileW) {
-                    const int u = tx0 + j - L.bx;
-                    s_col[slot][j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
-                } else {
-                    const int v = ty0 + (j - kTileW) - L.by;
-                    s_row[slot][j - kTileW] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
-                }
-            }
-            for (int i = tid; i < n_here * 256; i += kWarps * 32) {
-                const int slot = i >> 8, a = i & 255;
-                if (s_empty[base + slot]) continue;
-                const DevLayer& L = P.layers[s_active[base + slot]];
-                uint32_t v = (uint32_t)a;
-                if (L.opacity < 1.0)
-                    v = L.pil ? (uint32_t)(a * L.pil_a) / 255u                      // imgproc.py:206-208
-                              : __double2uint_rz(__dmul_rn((double)a, L.opacity));  // imgproc.py:159
-                s_lut[slot][a] = (uint8_t)v;
-            }
-            __syncthreads();
-            if (!x_ok) continue;
+        if (!x_ok) continue;
 
 #pragma unroll 1
-            for (int slot = 0; slot < n_here; ++slot) {
-                const int li = s_active[base + slot];
-                const DevLayer& L = P.layers[li];
+        for (int slot = 0; slot < n_here; ++slot) {
+            const DevLayer& L = P.layers[s_active[base + slot]];
+            const int cls = s_class[base + slot];
+            int r0 = rbeg, r1 = rend;
+            if (cls != kTileInterior) {
                 if ((unsigned)(x - L.bx) >= (unsigned)L.bw) continue;
-                const int r0 = max(rbeg, L.by - ty0), r1 = min(rend, L.by + L.bh - ty0);
+                r0 = max(rbeg, L.by - ty0);
+                r1 = min(rend, L.by + L.bh - ty0);
                 if (r0 >= r1) continue;
-                const int code = L.pil ? kPilOver : L.mode;
-                if (s_empty[base + slot]) { // numpy path, every sample transparent (imgproc.py:164)
-                    for (int row = r0; row < r1; ++row) {
-                        const uint32_t px = pxcol[row * kTileW];
-                        if (px < 0x01000000u && px != 0) pxcol[row * kTileW] = 0;
-                    }
-                    continue;
-                }
+            }
+            if (cls == kTileEmpty) { // numpy path on a non-opaque frame, every sample transparent
+                for (int row = r0; row < r1; ++row)
+                    if (pxcol[row * kTileW] < 0x01000000u) pxcol[row * kTileW] = 0;
+                continue;
+            }
+            // phase 1: sample the layer at the thread's pixels (mode-independent code)
+            {
                 const uint8_t* __restrict__ src = L.src;
-                const int sw = L.src_w, sh = L.src_h, ss = L.src_stride;
+                const int ss = L.src_stride;
                 const int2 col = s_col[slot][lane];
                 const int2* __restrict__ rowtab = s_row[slot];
                 const uint8_t* __restrict__ lut = s_lut[slot];
-#pragma unroll 1
-                for (int row = r0; row < r1; ++row) {
-                    const int2 r = rowtab[row];
-                    const int X = (r.x + col.x) >> 5, Y = (r.y + col.y) >> 5;
-                    const uint32_t px = pxcol[row * kTileW];
-                    Rgba s;
-                    uint32_t fa = 0;
-                    if (sample_q5(src, sw, sh, ss, X, Y, s)) fa = lut[s.a];
-                    uint32_t out;
-                    if (fa == 0) {
-                        // PIL: no-op.  numpy: no-op unless bg alpha is 0, where rgb is zeroed (imgproc.py:164)
-                        if (code == kPilOver || px >= 0x01000000u || px == 0) continue;
-                        out = 0;
-                    } else if (px < 0xFF000000u) {
-                        out = over_general(code, px, pack(s.r, s.g, s.b, fa));
-                    } else {
-                        switch (code) {
-#define MVB_CASE(M) case M: out = blend_opaque<M>(px, s, fa); break;
-                            MVB_CASE(0) MVB_CASE(1) MVB_CASE(2) MVB_CASE(3) MVB_CASE(4) MVB_CASE(5) MVB_CASE(6)
-                            MVB_CASE(7) MVB_CASE(8) MVB_CASE(9) MVB_CASE(10) MVB_CASE(11) MVB_CASE(12)
-                            MVB_CASE(13) MVB_CASE(14) MVB_CASE(15) MVB_CASE(16) MVB_CASE(17)
-#undef MVB_CASE
-                        default: out = blend_opaque<kPilOver>(px, s, fa); break;
-                        }
+                if (cls == kTileInterior) {
+#pragma unroll 4
+                    for (int row = r0; row < r1; ++row) {
+                        const int2 r = rowtab[row];
+                        const int X = (r.x + col.x) >> 5, Y = (r.y + col.y) >> 5;
+                        const uint8_t* base = src + ((uint32_t)(Y >> 5) * (uint32_t)ss + (uint32_t)(X >> 5) * 4u);
+                        const uint32_t p00 = ldg_u32(base), p01 = ldg_u32(base + 4);
+                        const uint32_t p10 = ldg_u32(base + ss), p11 = ldg_u32(base + ss + 4);
+                        const Rgba s = bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
+                        smpcol[row * kTileW] = s.r | (s.g << 8) | (s.b << 16) | ((uint32_t)lut[s.a] << 24);
                     }
-                    pxcol[row * kTileW] = out;
+                } else {
+                    const int sw = L.src_w, sh = L.src_h;
+#pragma unroll 1
+                    for (int row = r0; row < r1; ++row) {
+                        const int2 r = rowtab[row];
+                        Rgba s;
+                        uint32_t sp = 0;
+                        if (sample_q5(src, sw, sh, ss, (r.x + col.x) >> 5, (r.y + col.y) >> 5, s))
+                            sp = s.r | (s.g << 8) | (s.b << 16) | ((uint32_t)lut[s.a] << 24);
+                        smpcol[row * kTileW] = sp;
+                    }
                 }
             }
+            // phase 2: blend, in the loop specialised for this layer's mode
+            switch (L.pil ? kPilOver : L.mode) {
+#define MVB_ROWS(M) case M: blend_rows<M, OPAQUE>(smpcol, pxcol, r0, r1, tabs); break;
+                MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
+                MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
+                MVB_ROWS(15) MVB_ROWS(16) MVB_ROWS(17) MVB_ROWS(18)
+#undef MVB_ROWS
+            default: break;
+            }
         }
-
-        // ---- epilogue: one coalesced 128-byte store per warp row -----------------------------------
-        if (x_ok)
-            for (int row = rbeg; row < rend; ++row)
-                reinterpret_cast<uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x] = pxcol[row * kTileW];
     }
+
+    // ---- epilogue: one coalesced 128-byte store per warp row ---------------------------------------
+    if (x_ok)
+        for (int row = rbeg; row < rend; ++row)
+            reinterpret_cast<uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x] = pxcol[row * kTileW];
 }
 
 // cv2.warpAffine stand-alone: one thread per destination pixel.
@@ -361,6 +405,31 @@ static int check_image(const void* p, int w, int h, int64_t stride, const char* 
     return 0;
 }
 
+static int upload_blend_tables()
+{
+    static thread_local int uploaded_dev = -1;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev == uploaded_dev) return MVB_OK;
+    static BlendTableData t;
+    for (uint32_t d = 1; d <= 256; d++) t.rcp24[d] = (uint32_t)(((1ull << 24) + d - 1) / d);
+    t.rcp24[0] = 0;
+    for (int i = 257; i < 260; i++) t.rcp24[i] = 0;
+    for (uint32_t b = 0; b < 256; b++) { // g_w3c of imgproc.py:64-68 under uint32 wrap-around
+        if (b < 64) {
+            uint32_t v = 16u * b - 780300u * b + 260100u;
+            v *= b;
+            t.softg[b] = v / 65025u;
+        } else {
+            t.softg[b] = (uint32_t)std::sqrt((double)(255u * b));
+        }
+    }
+    cudaError_t e = cudaMemcpyToSymbol(g_blend_tables, &t, sizeof t);
+    if (e != cudaSuccess) return set_error(MVB_ERR_CUDA, cudaGetErrorString(e));
+    uploaded_dev = dev;
+    return MVB_OK;
+}
+
 static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t bg[4], int n_layers,
                         const mvb_layer* layers, int flags, cudaStream_t stream)
 {
@@ -370,6 +439,11 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
     P.H = H;
     P.stride = (int32_t)stride;
     std::memcpy(&P.bg, bg, 4);
+    P.pad_ = 0;
+    if (int rc = upload_blend_tables()) return rc;
+    // An opaque bg_color keeps the frame's alpha at 255 through every layer (both "over" operators
+    // map dst alpha 255 to 255), so the division-free kernel instantiation applies.
+    const bool opaque = bg[3] == 255 && !(flags & MVB_STACK_KEEP_FRAME);
     const dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH);
     int done = 0;
     bool first = true;
@@ -381,7 +455,13 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
         }
         P.n_layers = n;
         P.keep_frame = (!first || (flags & MVB_STACK_KEEP_FRAME)) ? 1 : 0;
-        k_composite_stack<<<grid, kWarps * 32, 0, stream>>>(P);
+        P.needs_tables = 0;
+        for (int i = 0; i < n; i++) {
+            const int m = P.layers[i].mode;
+            if (!P.layers[i].pil && (m == 6 || m == 7 || m == 11 || m == 12)) P.needs_tables = 1;
+        }
+        if (opaque) k_composite_stack<true><<<grid, kWarps * 32, 0, stream>>>(P);
+        else k_composite_stack<false><<<grid, kWarps * 32, 0, stream>>>(P);
         done += n;
         first = false;
     } while (done < n_layers);

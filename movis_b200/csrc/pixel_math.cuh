@@ -104,6 +104,40 @@ __device__ __forceinline__ uint32_t blend_target(uint32_t b, uint32_t f)
     else return (uint32_t)max(0, (int)b - (int)f);                       // subtract
 }
 
+// Table-assisted blend targets for the fused kernel.  The four division / sqrt heavy modes read
+//   rcp24[d] = ceil(2^24 / d), d in 1..256:  floor(n / d) == umulhi(n << 8, rcp24[d]) for n <= 65025
+//              (error term n * (rcp24[d] * d - 2^24) < 2^24, checked in tests/test_oracle_golden.py)
+//   softg[b] = g_w3c(b) of soft_light (imgproc.py:64-68), incl. its uint32 wrap-around for b < 64
+// from shared memory; every other mode is the closed form of blend_target<MODE>.
+struct BlendTables {
+    const uint32_t* rcp24; // 257 entries
+    const uint32_t* softg; // 256 entries
+};
+
+__device__ __forceinline__ uint32_t ratio255_tab(uint32_t num, uint32_t den, const uint32_t* rcp24)
+{
+    return min(__umulhi(num << 8, rcp24[den]), 255u);
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t blend_target_tab(uint32_t b, uint32_t f, const BlendTables& t)
+{
+    if constexpr (MODE == 6) return ratio255_tab(255 * b, 256 - f, t.rcp24);
+    else if constexpr (MODE == 7) return 255 - ratio255_tab(255 * (255 - b), f + 1, t.rcp24);
+    else if constexpr (MODE == 12) {
+        const uint32_t q = 255 - ratio255_tab(255 * (255 - b), (2 * f + 1) & 255u, t.rcp24);
+        return f > 127 ? 0u : q;
+    } else if constexpr (MODE == 11) {
+        const uint32_t td = (255u - 2u * f) * b * (255u - b); // meaningful for f < 128 only
+        const uint32_t dark = (b - td / 65025u) & 0xFFu;
+        const int32_t n = (int32_t)(2u * f - 255u) * ((int32_t)t.softg[b] - (int32_t)b);
+        int32_t q = n / 255;
+        q -= (n - q * 255) < 0; // floor division
+        const uint32_t light = (uint32_t)((int32_t)b + q) & 0xFFu;
+        return f < 128 ? dark : light;
+    } else return blend_target<MODE>(b, f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // "over" operators on packed RGBA (byte 0 = R ... byte 3 = A)
 // ---------------------------------------------------------------------------------------------
@@ -214,32 +248,48 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p)
     return __ldg(reinterpret_cast<const unsigned int*>(p));
 }
 
-// Sample `src` at fixed-point (X, Y) with 5 fractional bits; taps outside the image read 0
-// (BORDER_CONSTANT).  Returns false when all four taps are outside (sample is transparent black).
-// Byte offsets are 32-bit: a source image is < 2 GiB (checked on the host).
-__device__ __forceinline__ bool sample_q5(const uint8_t* __restrict__ src, int sw, int sh, int stride,
-                                          int X, int Y, Rgba& out)
-{
-    const int sx = X >> 5, sy = Y >> 5;
-    const uint32_t fx = X & 31, fy = Y & 31;
+// The four taps of one bilinear sample plus its 5-bit fractions, fetched ahead of their use.
+struct Taps {
     uint32_t p00, p01, p10, p11;
+    uint32_t fx, fy;
+    bool any; // false: all four taps are outside the image (sample is transparent black)
+};
+
+// Fetch the taps at fixed-point (X, Y) with 5 fractional bits; taps outside the image read 0
+// (BORDER_CONSTANT).  Byte offsets are 32-bit: a source image is < 4 GiB (checked on the host).
+__device__ __forceinline__ Taps fetch_taps(const uint8_t* __restrict__ src, int sw, int sh, int stride, int X, int Y)
+{
+    Taps t;
+    const int sx = X >> 5, sy = Y >> 5;
+    t.fx = X & 31;
+    t.fy = Y & 31;
+    t.any = true;
     if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
         const uint8_t* base = src + ((uint32_t)sy * (uint32_t)stride + (uint32_t)sx * 4u);
-        p00 = ldg_u32(base);
-        p01 = ldg_u32(base + 4);
-        p10 = ldg_u32(base + stride);
-        p11 = ldg_u32(base + stride + 4);
+        t.p00 = ldg_u32(base);
+        t.p01 = ldg_u32(base + 4);
+        t.p10 = ldg_u32(base + stride);
+        t.p11 = ldg_u32(base + stride + 4);
     } else {
         const bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
         const bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;
-        if (!((x0 | x1) & (y0 | y1))) return false;
+        t.any = (x0 | x1) & (y0 | y1);
         const uint8_t* base = src + (int64_t)sy * stride + (int64_t)sx * 4;
-        p00 = (x0 & y0) ? ldg_u32(base) : 0u;
-        p01 = (x1 & y0) ? ldg_u32(base + 4) : 0u;
-        p10 = (x0 & y1) ? ldg_u32(base + stride) : 0u;
-        p11 = (x1 & y1) ? ldg_u32(base + stride + 4) : 0u;
+        t.p00 = (x0 & y0) ? ldg_u32(base) : 0u;
+        t.p01 = (x1 & y0) ? ldg_u32(base + 4) : 0u;
+        t.p10 = (x0 & y1) ? ldg_u32(base + stride) : 0u;
+        t.p11 = (x1 & y1) ? ldg_u32(base + stride + 4) : 0u;
     }
-    out = bilinear_q5(p00, p01, p10, p11, fx, fy); // fx == fy == 0 reproduces p00 exactly
+    return t;
+}
+
+// Sample `src` at fixed-point (X, Y); returns false when all four taps are outside the image.
+__device__ __forceinline__ bool sample_q5(const uint8_t* __restrict__ src, int sw, int sh, int stride,
+                                          int X, int Y, Rgba& out)
+{
+    const Taps t = fetch_taps(src, sw, sh, stride, X, Y);
+    if (!t.any) return false;
+    out = bilinear_q5(t.p00, t.p01, t.p10, t.p11, t.fx, t.fy); // fx == fy == 0 reproduces p00 exactly
     return true;
 }
 
