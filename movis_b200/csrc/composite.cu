@@ -246,15 +246,31 @@ k_composite_stack(const __grid_constant__ StackParams P)
                 const int2* __restrict__ rowtab = s_row[slot];
                 const uint8_t* __restrict__ lut = s_lut[slot];
                 if (cls == kTileInterior) {
-#pragma unroll 4
-                    for (int row = r0; row < r1; ++row) {
-                        const int2 r = rowtab[row];
-                        const int X = (r.x + col.x) >> 5, Y = (r.y + col.y) >> 5;
-                        const uint8_t* base = src + ((uint32_t)(Y >> 5) * (uint32_t)ss + (uint32_t)(X >> 5) * 4u);
-                        const uint32_t p00 = ldg_u32(base), p01 = ldg_u32(base + 4);
-                        const uint32_t p10 = ldg_u32(base + ss), p11 = ldg_u32(base + ss + 4);
-                        const Rgba s = bilinear_q5(p00, p01, p10, p11, X & 31, Y & 31);
-                        smpcol[row * kTileW] = s.r | (s.g << 8) | (s.b << 16) | ((uint32_t)lut[s.a] << 24);
+                    // all kRows rows, every tap inside the source: 4 rows at a time, their 16 taps
+                    // requested before the first one is used
+#pragma unroll 1
+                    for (int g = 0; g < kRows; g += 4) {
+                        uint32_t t[4][4], fx[4], fy[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int2 r = rowtab[rbeg + g + k];
+                            const int X = (r.x + col.x) >> 5, Y = (r.y + col.y) >> 5;
+                            const uint8_t* base = src + ((uint32_t)(Y >> 5) * (uint32_t)ss + (uint32_t)(X >> 5) * 4u);
+                            t[k][0] = ldg_u32(base);
+                            t[k][1] = ldg_u32(base + 4);
+                            t[k][2] = ldg_u32(base + ss);
+                            t[k][3] = ldg_u32(base + ss + 4);
+                            fx[k] = X & 31;
+                            fy[k] = Y & 31;
+                        }
+                        Rgba q[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) q[k] = bilinear_q5(t[k][0], t[k][1], t[k][2], t[k][3], fx[k], fy[k]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) q[k].a = lut[q[k].a];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            smpcol[(rbeg + g + k) * kTileW] = q[k].r | (q[k].g << 8) | (q[k].b << 16) | (q[k].a << 24);
                     }
                 } else {
                     const int sw = L.src_w, sh = L.src_h;
