@@ -289,6 +289,8 @@ def cpu_baseline(sample_frames: int) -> dict:
     from movis_b200 import scenes
     from oracle import oracle as O
     from oracle import scene_eval
+    # torchrun exports OMP_NUM_THREADS=1; the baseline is meant to use every host thread we may run on
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     comp = scenes.build_s2(mv, div=1, variant=0)
     times = (np.arange(sample_frames) * 25 % 150) / FPS
     scene_eval.render(comp, float(times[0]), (0, 0, 0, 255))  # warm up (page in sources)

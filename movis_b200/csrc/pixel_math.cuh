@@ -14,8 +14,8 @@ namespace mvb {
 // small exact divisions
 // ---------------------------------------------------------------------------------------------
 
-// x / 255 for 0 <= x < 65536
-__device__ __forceinline__ uint32_t div255(uint32_t x) { return (x * 0x8081u) >> 23; }
+// x / 255 for 0 <= x < 2^24: one IMAD.HI (ceil(2^32 / 255) = 0x01010102, error term 254 x < 2^32)
+__device__ __forceinline__ uint32_t div255(uint32_t x) { return __umulhi(x, 0x01010102u); }
 
 // x / 255 for any 32-bit x
 __device__ __forceinline__ uint32_t div255_wide(uint32_t x) { return __umulhi(x, 0x80808081u) >> 7; }

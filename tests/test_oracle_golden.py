@@ -117,10 +117,10 @@ def test_affine_geometry(golden):
 
 def test_division_shortcuts_are_exact():
     """The two division shortcuts the CUDA kernels rely on, checked exhaustively on the CPU:
-    x // 255 == (x * 0x8081) >> 23 for x < 65536, and the float-reciprocal quotient estimate is
+    x // 255 == umulhi(x, 0x01010102) for x < 2^24, and the float-reciprocal quotient estimate is
     within +-1 of floor(n / d) for every (oa, quotient boundary) pair of the numpy 'over'."""
-    x = np.arange(65536, dtype=np.uint64)
-    assert np.array_equal(x // 255, (x * 0x8081) >> 23)
+    x = np.arange(1 << 24, dtype=np.uint64)
+    assert np.array_equal(x // 255, (x * 0x01010102) >> 32)   # div255() = umulhi(x, 0x01010102)
     d = np.arange(255, 65026, dtype=np.int64)
     rd = (np.float32(1.0) / d.astype(np.float32))
     for q in (1, 2, 127, 128, 254, 255):
@@ -151,3 +151,12 @@ def test_scene_walker_matches_reference_frames(golden):
                     assert np.array_equal(got, g[key]), key
                 n += 1
     assert n == 68
+
+
+def test_reciprocal_table_division_is_exact():
+    """The fused kernel divides by d in 1..256 with umulhi(n << 8, ceil(2^24 / d)) for n <= 65025
+    (color_dodge / color_burn / vivid_light, movis_b200/csrc/pixel_math.cuh): exhaustive check."""
+    n = np.arange(65026, dtype=np.uint64)
+    for d in range(1, 257):
+        m = np.uint64(((1 << 24) + d - 1) // d)
+        assert np.array_equal(((n << np.uint64(8)) * m) >> np.uint64(32), n // np.uint64(d)), d
