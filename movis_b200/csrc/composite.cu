@@ -111,6 +111,12 @@ __device__ __forceinline__ void blend_rows(const uint32_t* __restrict__ smpcol, 
 
 enum { kTileEdge = 0, kTileEmpty = 1, kTileInterior = 2 };
 
+} // namespace mvb
+
+#include "stack_float.cuh"   // k_stack_opaque: the float-arithmetic instantiation for opaque frames
+
+namespace mvb {
+
 // One CTA per kTileW x kTileH output tile (thread = 1 column x kRows rows).
 template <bool OPAQUE>
 __global__ void __launch_bounds__(kWarps * 32)
@@ -476,7 +482,7 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
             const int m = P.layers[i].mode;
             if (!P.layers[i].pil && (m == 6 || m == 7 || m == 11 || m == 12)) P.needs_tables = 1;
         }
-        if (opaque) k_composite_stack<true><<<grid, kWarps * 32, 0, stream>>>(P);
+        if (opaque) k_stack_opaque<<<grid, kFWarps * 32, 0, stream>>>(P);
         else k_composite_stack<false><<<grid, kWarps * 32, 0, stream>>>(P);
         done += n;
         first = false;
