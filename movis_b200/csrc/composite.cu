@@ -16,9 +16,15 @@
 //               memory, then jumps once to the blend loop specialised for the layer's mode;
 //   epilogue  - one coalesced 128-byte store per warp row.  The frame is written exactly once.
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
+
+#include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
 
 #include "../../include/movis_b200.h"
 #include "host_util.h"
@@ -34,17 +40,21 @@ constexpr int kMaxLayers = 32; // per launch; 32 * 104 B of descriptors stay und
 constexpr int kSlots = 16;     // layers whose per-tile tables are resident in shared memory at a time
 
 struct DevLayer {
-    const uint8_t* src;
-    int32_t src_w, src_h;
-    int32_t src_stride;
-    int32_t mode;       // MVB_BLEND_*
-    double m[6];        // inverse map: bbox px -> layer px (OpenCV's own inversion, done on host)
+    // --- first 64 bytes: what the per-tile cull / classification reads (copied to shared memory) ---
     int32_t bx, by, bw, bh;
-    double opacity;
+    int32_t src_w, src_h;
+    int32_t box_w, box_h; // TMA box (source px) that covers the footprint of any 32 x 32 tile; 0: no TMA
+    float mf[6];        // m rounded to float, for the cull only
+    int32_t mode;       // MVB_BLEND_*
     int32_t pil;        // 1: PIL over
+    // --- the rest ---
+    const uint8_t* src;
+    int32_t src_stride;
     int32_t pil_a;      // int(round(opacity * 255)) for the PIL path (imgproc.py:207)
+    double m[6];        // inverse map: bbox px -> layer px (OpenCV's own inversion, done on host)
+    double opacity;
 };
-static_assert(sizeof(DevLayer) == 104, "descriptor layout");
+static_assert(sizeof(DevLayer) == 136 && offsetof(DevLayer, src) == 64, "descriptor layout");
 
 struct StackParams {
     uint8_t* frame;
@@ -56,6 +66,16 @@ struct StackParams {
     int32_t needs_tables; // some layer uses color_dodge / color_burn / soft_light / vivid_light
     int32_t pad_;
     DevLayer layers[kMaxLayers];
+};
+
+// Parameters of the opaque-frame kernel: the stack plus one TMA descriptor per layer (a 2-D tiled
+// map over the layer's source image, box = DevLayer::box_w x box_h pixels, out-of-bounds = 0).
+struct StackParamsTma {
+    StackParams s;
+    int32_t stage_bytes;   // bytes of one shared-memory stage (the largest box of this launch)
+    int32_t stages_log2;   // 1 or 2: two or four stages in flight
+    int32_t pad_[14];
+    alignas(64) CUtensorMap maps[kMaxLayers];
 };
 
 constexpr int kPilOver = 18; // dispatch code of PIL's "over" next to the 18 numpy blend modes
@@ -413,6 +433,8 @@ static int fill_dev_layer(const mvb_layer& in, DevLayer& out)
     out.opacity = in.opacity;
     out.pil = (in.flags & MVB_LAYER_PIL_OVER) ? 1 : 0;
     out.pil_a = (int32_t)std::nearbyint(in.opacity * 255.0);
+    out.box_w = out.box_h = 0;
+    for (int i = 0; i < 6; i++) out.mf[i] = (float)out.m[i];
     return 0;
 }
 
@@ -452,10 +474,91 @@ static int upload_blend_tables()
     return MVB_OK;
 }
 
+// ---- TMA descriptors for layer sources ----------------------------------------------------------
+constexpr int kMaxStageBytes = 16384;   // per shared-memory stage: boxes up to 64 x 64 px
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// The box a 32 x 32 output tile needs from the source: extent of the tile under the inverse map
+// (|m0| + |m1|) * 31 plus the second tap and the 1/32 px quantisation (5 px), plus up to 3 px
+// because the box must start on a 16-byte boundary of the source row; width a multiple of 8 px
+// and height a multiple of 4 so animated scales share a few descriptors.
+static void choose_box(DevLayer& L)
+{
+    L.box_w = L.box_h = 0;
+    static const bool disabled = std::getenv("MVB_DISABLE_TMA") != nullptr;   // diagnostics: gather through L1 instead
+    if (disabled) return;
+    if ((reinterpret_cast<uintptr_t>(L.src) & 15) || (L.src_stride & 15)) return;   // TMA alignment rules
+    const double ex = 31.0 * (std::fabs(L.m[0]) + std::fabs(L.m[1]));
+    const double ey = 31.0 * (std::fabs(L.m[3]) + std::fabs(L.m[4]));
+    if (!(ex < 250.0 && ey < 250.0)) return;
+    const int bw = (((int)std::ceil(ex) + 8) + 7) & ~7, bh = (((int)std::ceil(ey) + 5) + 3) & ~3;
+    if (bw > 256 || bh > 256 || bw * bh * 4 > kMaxStageBytes) return;
+    L.box_w = bw;
+    L.box_h = bh;
+}
+
+struct MapKey {
+    const void* src; int32_t w, h, stride, bw, bh;
+    bool operator==(const MapKey& o) const
+    { return src == o.src && w == o.w && h == o.h && stride == o.stride && bw == o.bw && bh == o.bh; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const
+    {
+        uint64_t x = reinterpret_cast<uintptr_t>(k.src) * 0x9E3779B97F4A7C15ull;
+        x ^= ((uint64_t)(uint32_t)k.w << 32 | (uint32_t)k.h) * 0xC2B2AE3D27D4EB4Full;
+        x ^= ((uint64_t)(uint32_t)k.stride << 20 ^ (uint64_t)k.bw << 10 ^ (uint64_t)k.bh) * 0x165667B19E3779F9ull;
+        return (size_t)(x ^ (x >> 29));
+    }
+};
+
+// A descriptor is a pure function of its key, so entries never go stale; the cache is only bounded.
+static bool tensor_map_for(const DevLayer& L, CUtensorMap* out)
+{
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{L.src, L.src_w, L.src_h, L.src_stride, L.box_w, L.box_h};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)L.src_w, (cuuint64_t)L.src_h};
+    const cuuint64_t strides[1] = {(cuuint64_t)L.src_stride};
+    const cuuint32_t box[2] = {(cuuint32_t)L.box_w, (cuuint32_t)L.box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(L.src), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return true;
+}
+
 static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t bg[4], int n_layers,
                         const mvb_layer* layers, int flags, cudaStream_t stream)
 {
-    StackParams P;
+    static thread_local StackParamsTma PT;   // 7.6 KB: kept off the stack, reused between launches
+    StackParams& P = PT.s;
     P.frame = static_cast<uint8_t*>(frame);
     P.W = W;
     P.H = H;
@@ -482,8 +585,27 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
             const int m = P.layers[i].mode;
             if (!P.layers[i].pil && (m == 6 || m == 7 || m == 11 || m == 12)) P.needs_tables = 1;
         }
-        if (opaque) k_stack_opaque<<<grid, kFWarps * 32, 0, stream>>>(P);
-        else k_composite_stack<false><<<grid, kWarps * 32, 0, stream>>>(P);
+        if (opaque) {
+            int stage = 0;
+            for (int i = 0; i < n; i++) {
+                DevLayer& L = P.layers[i];
+                choose_box(L);
+                if (L.box_w && !tensor_map_for(L, &PT.maps[i])) L.box_w = L.box_h = 0;
+                if (L.box_w && L.box_w * L.box_h * 4 > stage) stage = L.box_w * L.box_h * 4;
+            }
+            static thread_local int smem_dev = -1;   // static + dynamic shared memory can exceed 48 KB: opt in once
+            int dev = -1;
+            cudaGetDevice(&dev);
+            if (dev != smem_dev) {
+                cudaFuncSetAttribute(k_stack_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxStageBytes);
+                smem_dev = dev;
+            }
+            PT.stage_bytes = (stage + 127) & ~127;
+            PT.stages_log2 = 4 * PT.stage_bytes <= 36 * 1024 ? 2 : 1;   // keep 4 CTAs per SM resident
+            k_stack_opaque<<<grid, kFWarps * 32, PT.stage_bytes << PT.stages_log2, stream>>>(PT);
+        } else {
+            k_composite_stack<false><<<grid, kWarps * 32, 0, stream>>>(P);
+        }
         done += n;
         first = false;
     } while (done < n_layers);

@@ -84,90 +84,121 @@ __device__ __forceinline__ float lds_f32(uint32_t shared_addr)
 }
 
 // ---------------------------------------------------------------------------------------------
-// T(b, f) - b for one lane, biased inputs (dB = magic + b, sB = magic + f): the blend targets of
-// movis/imgproc.py:11-133 in the closed forms of SURVEY.md 8(a-5), minus the background.
+// Blend + composite of one colour channel of two rows.  Inputs are biased (dB = magic + b,
+// sB = magic + f); `diff` below is T(b, f) - b with T the blend target of movis/imgproc.py:11-133
+// in the closed forms of SURVEY.md 8(a-5).  Two algebraic identities keep the product modes short
+// (N integer => floor(N + x) = N + floor(x)):
+//   screen   255 - floor((255-b)(255-f)/255)   = b + f - floor(b f / 255)
+//   overlay  255 - floor(2(255-b)(255-f)/255)  = 2b + 2f - 255 - floor(2 b f / 255)     (b >= 128)
 // ---------------------------------------------------------------------------------------------
 
-// min(255, floor(num255 / den)) + magic, num255 = 255 * n (n <= 255), 1 <= den <= 256.  The
-// quotient of (num + 0.5) by den is at least 0.5/256 away from every integer, MUFU.RCP and the
-// multiply are within 2^-22 relative, and only quotients below 256 matter (the rest clamp).
-__device__ __forceinline__ float ratio255_biased(float n, float den)
+__device__ __forceinline__ u64 add2_rm(u64 a, u64 b)
 {
-    const float t = fmaf(n, 255.0f, 0.5f) * rcp_approx(den);
-    return fminf(__fadd_rd(t, kMagic), kMagic + 255.0f);
+    u64 d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// f32x2 has no min / max: two scalar FMNMX on the halves of the register pair
+__device__ __forceinline__ u64 min2(u64 a, u64 b)
+{
+    float a0, a1, b0, b1;
+    upk(a, a0, a1);
+    upk(b, b0, b1);
+    return pk(fminf(a0, b0), fminf(a1, b1));
+}
+__device__ __forceinline__ u64 max2(u64 a, u64 b)
+{
+    float a0, a1, b0, b1;
+    upk(a, a0, a1);
+    upk(b, b0, b1);
+    return pk(fmaxf(a0, b0), fmaxf(a1, b1));
+}
+// per lane: key < thr ? a : b
+__device__ __forceinline__ u64 select_lt(u64 key, float thr, u64 a, u64 b)
+{
+    float k0, k1, a0, a1, b0, b1;
+    upk(key, k0, k1);
+    upk(a, a0, a1);
+    upk(b, b0, b1);
+    return pk(k0 < thr ? a0 : b0, k1 < thr ? a1 : b1);
+}
+__device__ __forceinline__ u64 rcp2(u64 a)
+{
+    float a0, a1;
+    upk(a, a0, a1);
+    return pk(rcp_approx(a0), rcp_approx(a1));
 }
 
-template <int MODE>
-__device__ __forceinline__ float blend_diff(float dB, float sB, const uint32_t* softg)
+// magic + min(255, floor(255 n / den)), n <= 255 plain, 1 <= den <= 256 plain.  The quotient of
+// (255 n + 0.5) by den is at least 0.5/256 away from every integer, MUFU.RCP and the multiply are
+// within 2^-22 relative, and only quotients below 256 matter (the rest clamp).
+__device__ __forceinline__ u64 ratio255_biased(u64 n, u64 den)
 {
-    if constexpr (MODE == 4) return fminf(sB, dB) - dB;                           // darken
-    else if constexpr (MODE == 5) return fmaxf(sB, dB) - dB;                      // lighten
-    else if constexpr (MODE == 3 || MODE == 10) {                                 // overlay / hard_light
-        const float b = dB - kMagic, f = sB - kMagic;
-        const float nb = 255.0f - b, nf = 255.0f - f;
-        const bool lo = (MODE == 3 ? b : f) < 128.0f;
-        const float bb = lo ? b : nb, ff = lo ? f : nf;
-        const float q = __fmaf_rd(bb * ff, 2.0f * kInv255, kMagic) - kMagic;      // floor(2 bb ff / 255)
-        const float t = q - bb;                                                   // lo: T - b; else -(T - b)
-        return lo ? t : -t;
-    } else if constexpr (MODE == 6) {                                             // color_dodge
-        return ratio255_biased(dB - kMagic, (kMagic + 256.0f) - sB) - dB;
-    } else if constexpr (MODE == 7) {                                             // color_burn
-        const float nb = (kMagic + 255.0f) - dB;
-        return (nb + kMagic) - ratio255_biased(nb, sB - (kMagic - 1.0f));         // 255 - q - b
-    } else if constexpr (MODE == 8) {                                             // linear_dodge
-        return fminf((kMagic + 255.0f) - dB, sB - kMagic);                        // min(255 - b, f)
-    } else if constexpr (MODE == 9) {                                             // linear_burn
-        return fmaxf(kMagic - dB, sB - (kMagic + 255.0f));                        // max(-b, f - 255)
-    } else if constexpr (MODE == 11) {                                            // soft_light (integer form)
-        const uint32_t bi = __float_as_uint(dB) & 0xFFu, fi = __float_as_uint(sB) & 0xFFu;
-        const BlendTables tabs{nullptr, softg};
-        return __uint_as_float(blend_target_tab<11>(bi, fi, tabs) | kMagicBits) - dB;
-    } else if constexpr (MODE == 12) {                                            // vivid_light (sic)
-        const float f = sB - kMagic;
-        const float nb = (kMagic + 255.0f) - dB;
-        const float d = (nb + kMagic) - ratio255_biased(nb, fmaf(f, 2.0f, 1.0f));
-        return f > 127.0f ? kMagic - dB : d;                                      // f > 127: T = 0
-    } else if constexpr (MODE == 13) {                                            // linear_light
-        const float g = fmaf(sB - kMagic, 2.0f, -255.0f);                         // clamp(b + 2f - 255, 0, 255) - b
-        return fminf(fmaxf(g, kMagic - dB), (kMagic + 255.0f) - dB);
-    } else if constexpr (MODE == 14) {                                            // pin_light
-        const float hB = fmaf(sB - kMagic, 2.0f, kMagic);                         // magic + 2f
-        return fminf(fmaxf(dB, hB - 255.0f), hB) - dB;                            // min(max(b, 2f - 255), 2f) - b
-    } else if constexpr (MODE == 15) {                                            // difference
-        return fabsf(dB - sB) - (dB - kMagic);
-    } else {                                                                      // subtract
-        static_assert(MODE == 17, "scalar blend_diff covers the min/max/select modes only");
-        return fmaxf(kMagic - dB, kMagic - sB);                                   // max(0, b - f) - b
-    }
+    const u64 t = mul2(fma2(n, bc(255.0f), bc(0.5f)), rcp2(den));
+    return min2(add2_rm(t, bc(kMagic)), bc(kMagic + 255.0f));
 }
 
-// One colour channel of two rows: blend + composite + requantise.  Returns magic + new value.
 template <int MODE>
 __device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const uint32_t* softg)
 {
+    const u64 kM = bc(kMagic), kM255 = bc(kMagic + 255.0f);
     u64 diff;
     if constexpr (MODE == 0 || MODE == 18) {                                      // normal / PIL over
         diff = sub2(sB, dB);
-    } else if constexpr (MODE == 1) {                                             // multiply
-        const u64 p = mul2(add2(dB, bc(-kMagic)), add2(sB, bc(-kMagic)));
-        diff = sub2(fma2_rm(p, bc(kInv255), bc(kMagic)), dB);
-    } else if constexpr (MODE == 2) {                                             // screen
-        const u64 nb = sub2(bc(kMagic + 255.0f), dB), nf = sub2(bc(kMagic + 255.0f), sB);
-        diff = sub2(add2(nb, bc(kMagic)), fma2_rm(mul2(nb, nf), bc(kInv255), bc(kMagic))); // 255 - q - b
-    } else if constexpr (MODE == 16) {                                            // exclusion: f - floor(2bf/255)
-        const u64 p = mul2(add2(dB, bc(-kMagic)), add2(sB, bc(-kMagic)));
-        diff = sub2(sB, fma2_rm(p, bc(2.0f * kInv255), bc(kMagic)));
-    } else {
+    } else if constexpr (MODE == 1 || MODE == 2 || MODE == 16) {                  // multiply / screen / exclusion
+        const u64 p = mul2(sub2(dB, kM), sub2(sB, kM));
+        const u64 qB = fma2_rm(p, bc(MODE == 16 ? 2.0f * kInv255 : kInv255), kM);
+        diff = MODE == 1 ? sub2(qB, dB) : sub2(sB, qB);                           // q - b  |  f - q
+    } else if constexpr (MODE == 3 || MODE == 10) {                               // overlay / hard_light
+        const u64 b = sub2(dB, kM), f = sub2(sB, kM);
+        const u64 qB = fma2_rm(mul2(b, f), bc(2.0f * kInv255), kM);               // floor(2 b f / 255)
+        const u64 lo = sub2(qB, dB);                                              // q - b
+        const u64 hi = sub2(fma2(f, bc(2.0f), sub2(dB, bc(255.0f))), qB);         // (b + 2f - 255) - q
+        diff = select_lt(MODE == 3 ? b : f, 128.0f, lo, hi);
+    } else if constexpr (MODE == 4) {                                             // darken: min(f - b, 0)
+        diff = min2(sub2(sB, dB), bc(0.0f));
+    } else if constexpr (MODE == 5) {                                             // lighten
+        diff = max2(sub2(sB, dB), bc(0.0f));
+    } else if constexpr (MODE == 6) {                                             // color_dodge: 255 b / (256 - f)
+        diff = sub2(ratio255_biased(sub2(dB, kM), sub2(bc(kMagic + 256.0f), sB)), dB);
+    } else if constexpr (MODE == 7) {                                             // color_burn: 255 - 255 (255-b) / (f+1)
+        const u64 nb = sub2(kM255, dB);
+        diff = sub2(add2(nb, kM), ratio255_biased(nb, sub2(sB, bc(kMagic - 1.0f))));  // 255 - q - b
+    } else if constexpr (MODE == 8) {                                             // linear_dodge: min(255 - b, f)
+        diff = min2(sub2(kM255, dB), sub2(sB, kM));
+    } else if constexpr (MODE == 9) {                                             // linear_burn: max(-b, f - 255)
+        diff = max2(sub2(kM, dB), sub2(sB, kM255));
+    } else if constexpr (MODE == 11) {                                            // soft_light (integer form)
         float d0, d1, s0, s1;
         upk(dB, d0, d1);
         upk(sB, s0, s1);
-        diff = pk(blend_diff<MODE>(d0, s0, softg), blend_diff<MODE>(d1, s1, softg));
+        const BlendTables tabs{nullptr, softg};
+        const uint32_t t0 = blend_target_tab<11>(__float_as_uint(d0) & 0xFFu, __float_as_uint(s0) & 0xFFu, tabs);
+        const uint32_t t1 = blend_target_tab<11>(__float_as_uint(d1) & 0xFFu, __float_as_uint(s1) & 0xFFu, tabs);
+        diff = sub2(pk(__uint_as_float(t0 | kMagicBits), __uint_as_float(t1 | kMagicBits)), dB);
+    } else if constexpr (MODE == 12) {                                            // vivid_light (sic)
+        const u64 f = sub2(sB, kM), nb = sub2(kM255, dB);
+        const u64 d = sub2(add2(nb, kM), ratio255_biased(nb, fma2(f, bc(2.0f), bc(1.0f))));
+        diff = select_lt(f, 127.5f, d, sub2(kM, dB));                             // f > 127: T = 0
+    } else if constexpr (MODE == 13) {                                            // linear_light
+        const u64 negb = sub2(kM, dB);                                            // clamp(2f - 255, -b, 255 - b)
+        diff = min2(max2(fma2(sub2(sB, kM), bc(2.0f), bc(-255.0f)), negb), add2(negb, bc(255.0f)));
+    } else if constexpr (MODE == 14) {                                            // pin_light
+        const u64 hB = fma2(sub2(sB, kM), bc(2.0f), kM);                          // magic + 2f
+        diff = sub2(min2(max2(dB, sub2(hB, bc(255.0f))), hB), dB);                // min(max(b, 2f - 255), 2f) - b
+    } else if constexpr (MODE == 15) {                                            // difference: |b - f| - b
+        float t0, t1, b0, b1;
+        upk(sub2(dB, sB), t0, t1);
+        upk(sub2(dB, kM), b0, b1);
+        diff = pk(fabsf(t0) - b0, fabsf(t1) - b1);
+    } else {                                                                      // subtract: max(-b, -f)
+        static_assert(MODE == 17, "unknown blend mode");
+        diff = max2(sub2(kM, dB), sub2(kM, sB));
     }
     // x = fa*T + (255 - fa)*b = fa*(T - b) + 255*b, an integer in [0, 65025]
     const u64 x = fma2(fa, diff, fma2(dB, bc(255.0f), bc(kNeg255Magic)));
-    if constexpr (MODE == 18) return fma2(x, bc(kInv255), bc(kMagic));            // PIL: floor((x+127)/255) = rint(x/255)
-    else return fma2_rm(x, bc(kInv255), bc(kMagic));                              // numpy: floor(x/255)
+    if constexpr (MODE == 18) return fma2(x, bc(kInv255), kM);                    // PIL: floor((x+127)/255) = rint(x/255)
+    else return fma2_rm(x, bc(kInv255), kM);                                      // numpy: floor(x/255)
 }
 
 constexpr int kFWarps = 8;   // 256 threads: 8 warps x 4 rows = one 32 x 32 tile
@@ -176,6 +207,16 @@ constexpr int kFTileH = kFWarps * kFRows;
 constexpr int kFSlots = 8;   // layers whose per-tile tables are resident in shared memory at a time
 
 struct RowPairState { u64 c[3]; };   // r, g, b of rows (2p, 2p+1), biased
+
+// Everything the layer loop reads about one resident layer, contiguous so that one base address
+// serves all of it (offsets become LDS immediates).
+struct __align__(16) SlotMem {
+    int4 info;               // see the table-building code
+    int4 box;                // bbox (x, y, w, h), for tiles the layer covers only partly
+    int2 col[kTileW];        // (adelta, bdelta) per tile column
+    int2 row[kFTileH];       // (X0, Y0) per tile row (relative to the box origin for TMA layers)
+    float lut[256];          // opacity-scaled alpha, as float
+};
 
 template <int MODE>
 __device__ __forceinline__ void blend_rows(RowPairState (&d)[2], const u64 (&s)[2][4], const u64 (&fa)[2],
@@ -187,57 +228,132 @@ __device__ __forceinline__ void blend_rows(RowPairState (&d)[2], const u64 (&s)[
         for (int c = 0; c < 3; ++c) d[p].c[c] = blend_chan<MODE>(d[p].c[c], s[p][c], fa[p], softg);
 }
 
-__global__ void __launch_bounds__(kFWarps * 32, 4)
-k_stack_opaque(const __grid_constant__ StackParams P)
+// ---- TMA / mbarrier plumbing (PTX; sm_90+ async proxy) -------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    __shared__ int2 s_col[kFSlots][kTileW];     // (adelta, bdelta) per tile column
-    __shared__ int2 s_row[kFSlots][kFTileH];    // (X0, Y0) per tile row
-    __shared__ float s_lut[kFSlots][256];       // opacity-scaled alpha, as float
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Blocks until the phase with the given parity has completed.  A wait that never completes means
+// a broken descriptor: trap instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1u << 22)) __trap();
+    }
+}
+// One box of the tiled tensor map -> shared memory; completion is signalled on `bar` (bytes).
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void* map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
+
+enum { kTileTma = 3 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
+
+// Position of the n-th (0-based) set bit of `mask` (n below its popcount, n small).
+__device__ __forceinline__ int nth_set_bit(unsigned mask, int n)
+{
+    for (int q = 0; q < n; ++q) mask &= mask - 1;
+    return __ffs((int)mask) - 1;
+}
+
+// One CTA per 32 x 32 output tile, 256 threads, thread = 1 column x 4 rows, pixels in registers.
+//
+// Source texels reach the SM through TMA: for every layer that touches the tile, one elected
+// thread requests the box of the source image that covers the tile's footprint (DevLayer::box_w
+// x box_h px at the tile's own origin, zero-filled outside the image = cv2's BORDER_CONSTANT)
+// into one of two shared-memory stages, one layer ahead of the arithmetic; the 4 taps of a
+// sample are then 4 LDS at tile-local offsets with no bounds logic.  Layers whose source is not
+// 16-byte aligned / too strongly minified for a stage gather through L1 instead (LDG).
+__global__ void __launch_bounds__(kFWarps * 32, 4)
+k_stack_opaque(const __grid_constant__ StackParamsTma PT)
+{
+    const StackParams& P = PT.s;
+    extern __shared__ __align__(1024) uint8_t s_stage[];   // 2 stages of PT.stage_bytes
+    __shared__ SlotMem s_slot[kFSlots];         // per resident layer: info, bbox, warp tables, alpha LUT
     __shared__ uint32_t s_softg[256];
-    __shared__ int s_active[kMaxLayers];
-    __shared__ int s_class[kMaxLayers];
-    __shared__ int s_nactive;
+    __shared__ __align__(8) unsigned long long s_bar[8];   // full[0..3], empty[0..3]
+    __shared__ int s_class[kMaxLayers];         // per layer: -1 (misses the tile) or kTile* | (partial coverage ? 256 : 0)
+    __shared__ int2 s_org[kMaxLayers];          // per layer: TMA box origin in source px
+    __shared__ int s_layer[kFSlots];            // per resident layer: layer index | index among the tile's TMA layers << 8
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kFTileH;
+    const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[4]);
+    const uint32_t stage0 = smem_addr(s_stage);
+    const int ns_log2 = PT.stages_log2, ns_mask = (1 << ns_log2) - 1;   // 2 or 4 stages
 
-    // ---- cull + classify the layers against this tile (as in k_composite_stack) -----------------
-    if (warp == 0) {
-        bool hit = false;
-        int cls = kTileEdge;
-        if (lane < P.n_layers) {
-            const DevLayer& L = P.layers[lane];
-            const int u0 = max(tx0, L.bx) - L.bx, u1 = min(min(tx0 + kTileW, L.bx + L.bw), P.W) - 1 - L.bx;
-            const int v0 = max(ty0, L.by) - L.by, v1 = min(min(ty0 + kFTileH, L.by + L.bh), P.H) - 1 - L.by;
-            hit = L.bw > 0 && L.bh > 0 && u0 <= u1 && v0 <= v1;
-            if (hit) {
-                double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    // ---- cull + classify the layers against this tile ---------------------------------------------
+    // Warp 0 classifies one layer per lane; the others meanwhile set up their pixels.
+    if (tid == 0) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const double u = (k & 1) ? u1 : u0, v = (k & 2) ? v1 : v0;
-                    const double xs = L.m[0] * u + L.m[1] * v + L.m[2];
-                    const double ys = L.m[3] * u + L.m[4] * v + L.m[5];
-                    xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
-                    ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
-                }
-                const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == kFTileH - 1;
-                if (xmax < -1.25 || xmin > L.src_w + 0.25 || ymax < -1.25 || ymin > L.src_h + 0.25)
-                    hit = false;           // no tap inside the source: a no-op on an opaque frame
-                else if (full && xmin > 0.25 && xmax < L.src_w - 1.25 && ymin > 0.25 && ymax < L.src_h - 1.25)
-                    cls = kTileInterior;   // whole tile covered and every tap inside the source
-            }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, kFWarps);
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) {
-            const int slot = __popc(m & ((1u << lane) - 1u));
-            s_active[slot] = lane;
-            s_class[slot] = cls;
-        }
-        if (lane == 0) s_nactive = __popc(m);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     s_softg[tid] = g_blend_tables.softg[tid];   // unconditional: a predicated LDG makes ptxas re-derive the
                                                 // global-memory descriptor (R2UR) in front of every load
+    if (warp == 0) {
+        int cls = -1;   // -1: the layer does not touch this tile
+        int2 org = make_int2(0, 0);
+        if (lane < P.n_layers) {
+            const DevLayer& L = P.layers[lane];
+            const int bx = L.bx, by = L.by, bw = L.bw, bh = L.bh, src_w = L.src_w, src_h = L.src_h;
+            const int box_w = L.box_w, box_h = L.box_h;
+            const float m0 = L.mf[0], m1 = L.mf[1], m2 = L.mf[2], m3 = L.mf[3], m4 = L.mf[4], m5 = L.mf[5];
+            // tile ∩ bbox ∩ frame, in bbox coordinates (inclusive corners)
+            const int u0 = max(tx0, bx) - bx, u1 = min(min(tx0 + kTileW, bx + bw), P.W) - 1 - bx;
+            const int v0 = max(ty0, by) - by, v1 = min(min(ty0 + kFTileH, by + bh), P.H) - 1 - by;
+            if (bw > 0 && bh > 0 && u0 <= u1 && v0 <= v1) {
+                // source-space extent of that rectangle (affine: centre +- sum |coef| * half size); 0.25 px
+                // of slack covers the 1/32 px coordinate quantisation and its +16/1024 rounding offset
+                // (fp32: positions below 32768 px are good to 0.01 px, far inside that slack)
+                const float uc = 0.5f * (float)(u0 + u1), vc = 0.5f * (float)(v0 + v1);
+                const float hu = 0.5f * (float)(u1 - u0), hv = 0.5f * (float)(v1 - v0);
+                const float xc = m0 * uc + m1 * vc + m2, ex = fabsf(m0) * hu + fabsf(m1) * hv;
+                const float yc = m3 * uc + m4 * vc + m5, ey = fabsf(m3) * hu + fabsf(m4) * hv;
+                const float xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
+                const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == kFTileH - 1;
+                // (no tap inside the source: a no-op on an opaque frame -> stays -1)
+                if (!(xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f)) {
+                    cls = kTileEdge;
+                    // taps span [floor(xmin) - 1, floor(xmax) + 2] at most (same slack as above); TMA wants
+                    // the box to start on a 16-byte boundary of the row: x origin a multiple of 4 px
+                    const int fx0 = ((int)floorf(xmin) - 1) & ~3, fy0 = (int)floorf(ymin) - 1;
+                    if (box_w > 0 && (int)floorf(xmax) + 3 - fx0 <= box_w && (int)floorf(ymax) + 3 - fy0 <= box_h) {
+                        cls = kTileTma | (full ? 0 : 256);
+                        org = make_int2(fx0, fy0);
+                    } else if (full && xmin > 0.25f && xmax < src_w - 1.25f && ymin > 0.25f && ymax < src_h - 1.25f) {
+                        cls = kTileInterior;   // whole tile covered and every tap inside the source
+                    }
+                }
+            }
+        }
+        s_class[lane] = cls;
+        s_org[lane] = org;
+    }
 
     // ---- the thread's pixels: column `lane`, rows [4 warp, 4 warp + 4), in registers --------------
     const int x = tx0 + lane;
@@ -260,46 +376,120 @@ k_stack_opaque(const __grid_constant__ StackParams P)
         for (int c = 0; c < 3; ++c) d[0].c[c] = d[1].c[c] = bc(kMagic + (float)((P.bg >> (8 * c)) & 0xFFu));
     }
     __syncthreads();
-    const int n_active = s_nactive;
+    // every warp derives the paint-ordered list of active layers from the class table by itself
+    const int my_cls = s_class[lane];
+    const unsigned m_act = __ballot_sync(0xFFFFFFFFu, my_cls >= 0);
+    const unsigned m_tma = __ballot_sync(0xFFFFFFFFu, my_cls >= 0 && (my_cls & 255) == kTileTma);
+    const int n_active = __popc(m_act);
+    const int n_tma = __popc(m_tma);
 
+    // Request the box of the k-th TMA layer of this tile into stage k mod n_stages (thread 0 only).
+    auto request = [&](int k) {
+        const int li = nth_set_bit(m_tma, k);
+        const DevLayer& L = P.layers[li];
+        const int2 org = s_org[li];
+        const uint32_t bar = bar_full + 8 * (k & ns_mask);
+        mbar_arrive_expect_tx(bar, (uint32_t)(L.box_w * L.box_h * 4));
+        tma_load_box(stage0 + (k & ns_mask) * PT.stage_bytes, &PT.maps[li], org.x, org.y, bar);
+    };
+    if (tid == 0)
+        for (int k = 0; k < min(n_tma, ns_mask + 1); ++k) request(k);
+
+    unsigned m_rest = m_act;   // active layers not yet walked, in paint order
     for (int base = 0; base < n_active; base += kFSlots) {
         const int n_here = min(kFSlots, n_active - base);
         if (base > 0) __syncthreads();
         for (int i = tid; i < n_here * (kTileW + kFTileH); i += kFWarps * 32) {
             const int slot = i / (kTileW + kFTileH), j = i % (kTileW + kFTileH);
-            const DevLayer& L = P.layers[s_active[base + slot]];
+            const int li = nth_set_bit(m_rest, slot);
+            const DevLayer& L = P.layers[li];
             if (j < kTileW) {
                 const int u = tx0 + j - L.bx;
-                s_col[slot][j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
+                s_slot[slot].col[j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
             } else {
                 const int v = ty0 + (j - kTileW) - L.by;
-                s_row[slot][j - kTileW] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
+                const int2 org = s_org[li];   // (0, 0) unless the layer is staged by TMA
+                s_slot[slot].row[j - kTileW] = make_int2(warp_x0(L.m, v) - org.x * 1024, warp_y0(L.m, v) - org.y * 1024);
             }
         }
-        for (int slot = 0; slot < n_here; ++slot) {   // 256 threads: one LUT entry each
-            const DevLayer& L = P.layers[s_active[base + slot]];
+        if (tid < n_here) {   // what the layer loop needs, one 16-byte read per layer
+            const int li = nth_set_bit(m_rest, tid);
+            const DevLayer& L = P.layers[li];
+            const int cls = s_class[li];
+            const int k = (cls & 255) == kTileTma ? __popc(m_tma & ((1u << li) - 1u)) : 0;
+            // x: mode (8 bits) | class (2) | partial coverage (bit 10) | phase parity (bit 11) |
+            //    refill: thread 0 re-arms the stage of TMA layer k-1 before this layer (bit 12) | row pitch << 16
+            // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]   w: stage address
+            const int refill = k >= 1 && k + ns_mask < n_tma;
+            s_slot[tid].info = make_int4((L.pil ? kPilOver : L.mode) | ((cls & 3) << 8) | ((cls >> 8) << 10) |
+                                        (((k >> ns_log2) & 1) << 11) | (refill << 12) | ((L.box_w * 4) << 16),
+                                    (int)(bar_full + 8 * (k & ns_mask)),
+                                    (int)(smem_addr(s_slot[tid].lut) - (kMagicBits << 2)),
+                                    (int)(stage0 + (k & ns_mask) * PT.stage_bytes));
+            s_slot[tid].box = make_int4(L.bx, L.by, L.bw, L.bh);
+            s_layer[tid] = li | (k << 8);
+        }
+        for (int slot = 0; slot < n_here; ++slot, m_rest &= m_rest - 1) {   // 256 threads: one LUT entry each
+            const DevLayer& L = P.layers[__ffs((int)m_rest) - 1];
             uint32_t v = (uint32_t)tid;
             if (L.opacity < 1.0)
                 v = L.pil ? (uint32_t)(tid * L.pil_a) / 255u                        // imgproc.py:206-208
                           : __double2uint_rz(__dmul_rn((double)tid, L.opacity));    // imgproc.py:159
-            s_lut[slot][tid] = (float)v;
+            s_slot[slot].lut[tid] = (float)v;
         }
         __syncthreads();
 
 #pragma unroll 1
         for (int slot = 0; slot < n_here; ++slot) {
-            const DevLayer& L = P.layers[s_active[base + slot]];
-            const int cls = s_class[base + slot];
-            const uint8_t* __restrict__ src = L.src;
-            const int ss = L.src_stride;
-            const int2 col = s_col[slot][lane];
-            const int2* __restrict__ rowtab = &s_row[slot][rbeg];
+            const SlotMem& S = s_slot[slot];
+            const int4 info = S.info;
+            const int cls = (info.x >> 8) & 3;
+            const bool part = info.x & (1 << 10);
+            const int2 col = S.col[lane];
+            const int2* __restrict__ rowtab = &S.row[rbeg];
 
             // ---- taps of the four rows, all requested before the first is used ----------------------
             uint32_t t[kFRows][4];
             float fxs[kFRows];
             uint32_t wy[kFRows];
-            if (cls == kTileInterior) {
+            unsigned ok = 0xFu;   // bit q: row q of this thread lies inside the layer's bbox and the frame
+            if (cls == kTileTma) {
+                if (tid == 0 && (info.x & (1 << 12))) {   // the stage of layer k-1 is free once every warp has read it
+                    const int k = s_layer[slot] >> 8;
+                    mbar_wait(bar_empty + 8 * ((k - 1) & ns_mask), ((k - 1) >> ns_log2) & 1);
+                    request(k + ns_mask);
+                }
+                const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
+                if (part) {
+                    const int4 bb = S.box;
+                    const bool col_in = x_ok && (unsigned)(x - bb.x) < (unsigned)bb.z;
+                    ok = 0;
+#pragma unroll
+                    for (int q = 0; q < kFRows; ++q) {
+                        const int yy = ty0 + rbeg + q;
+                        ok |= (col_in && (unsigned)(yy - bb.y) < (unsigned)bb.w && yy < P.H) ? (1u << q) : 0u;
+                    }
+                }
+                mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
+#pragma unroll
+                for (int q = 0; q < kFRows; ++q) {
+                    const int2 r = rowtab[q];
+                    const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
+                    uint32_t a = stage + (uint32_t)(sumy >> 10) * pitch + (uint32_t)(sumx >> 10) * 4u;
+                    if (part) a = (ok >> q & 1) ? a : stage;               // outside the bbox: any valid address; alpha is zeroed below
+                    t[q][0] = lds_u32(a);
+                    t[q][1] = lds_u32(a + 4);
+                    t[q][2] = lds_u32(a + pitch);
+                    t[q][3] = lds_u32(a + pitch + 4);
+                    fxs[q] = (float)(sumx & 0x3E0);                        // 32 * fx
+                    wy[q] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;     // bytes (32 - fy, fy, 0, 0)
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive((uint32_t)info.y + 32);         // this warp is done with the stage
+            } else if (cls == kTileInterior) {
+                const DevLayer& L = P.layers[s_layer[slot] & 255];
+                const uint8_t* __restrict__ src = L.src;
+                const int ss = L.src_stride;
 #pragma unroll
                 for (int k = 0; k < kFRows; ++k) {
                     const int2 r = rowtab[k];
@@ -309,10 +499,13 @@ k_stack_opaque(const __grid_constant__ StackParams P)
                     t[k][1] = ldg_u32(p + 4);
                     t[k][2] = ldg_u32(p + ss);
                     t[k][3] = ldg_u32(p + ss + 4);
-                    fxs[k] = (float)(sumx & 0x3E0);                        // 32 * fx
-                    wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;     // bytes (32 - fy, fy, 0, 0)
+                    fxs[k] = (float)(sumx & 0x3E0);
+                    wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
                 }
             } else {
+                const DevLayer& L = P.layers[s_layer[slot] & 255];
+                const uint8_t* __restrict__ src = L.src;
+                const int ss = L.src_stride;
                 const int sw = L.src_w, sh = L.src_h;
                 const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
 #pragma unroll
@@ -320,7 +513,7 @@ k_stack_opaque(const __grid_constant__ StackParams P)
                     const int2 r = rowtab[k];
                     const int sumx = r.x + col.x, sumy = r.y + col.y;
                     const int yy = ty0 + rbeg + k;
-                    t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0u;            // outside the bbox: fa = lut[0] = 0, a no-op
+                    t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0u;
                     if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) {
                         const Taps tp = fetch_taps(src, sw, sh, ss, sumx >> 5, sumy >> 5);
                         t[k][0] = tp.p00; t[k][1] = tp.p01; t[k][2] = tp.p10; t[k][3] = tp.p11;
@@ -333,7 +526,7 @@ k_stack_opaque(const __grid_constant__ StackParams P)
             // ---- cv2's fixed-point bilinear: out = (sum w p + 512) >> 10 -------------------------------
             u64 s[2][4], fa[2];
             // &lut[bits - kMagicBits] for the biased alpha `bits`: one LEA (the shift drops the exponent bits)
-            const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut[slot]) - (kMagicBits << 2);
+            const uint32_t lut_base = (uint32_t)info.z;
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 float vl[2][4], vr[2][4];
@@ -363,11 +556,16 @@ k_stack_opaque(const __grid_constant__ StackParams P)
                 }
                 float a0, a1;
                 upk(s[p][3], a0, a1);
-                fa[p] = pk(lds_f32(lut_base + (__float_as_uint(a0) << 2)), lds_f32(lut_base + (__float_as_uint(a1) << 2)));
+                uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);
+                if (part) {   // rows outside the bbox sampled a dummy address: alpha 0 -> lut[0] = 0 -> no-op
+                    i0 = (ok >> (2 * p) & 1) ? i0 : kMagicBits;
+                    i1 = (ok >> (2 * p + 1) & 1) ? i1 : kMagicBits;
+                }
+                fa[p] = pk(lds_f32(lut_base + (i0 << 2)), lds_f32(lut_base + (i1 << 2)));
             }
 
             // ---- blend, in the code specialised for this layer's mode ------------------------------------
-            switch (L.pil ? kPilOver : L.mode) {
+            switch (info.x & 255) {
 #define MVB_ROWS(M) case M: blend_rows<M>(d, s, fa, s_softg); break;
                 MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
                 MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
