@@ -134,6 +134,7 @@ enum { kTileEdge = 0, kTileEmpty = 1, kTileInterior = 2 };
 } // namespace mvb
 
 #include "stack_float.cuh"   // k_stack_opaque: the float-arithmetic instantiation for opaque frames
+#include "stack_ws.cuh"      // k_stack_ws: its persistent, warp-specialised form (default)
 
 namespace mvb {
 
@@ -593,16 +594,29 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
                 if (L.box_w && !tensor_map_for(L, &PT.maps[i])) L.box_w = L.box_h = 0;
                 if (L.box_w && L.box_w * L.box_h * 4 > stage) stage = L.box_w * L.box_h * 4;
             }
-            static thread_local int smem_dev = -1;   // static + dynamic shared memory can exceed 48 KB: opt in once
+            static thread_local int smem_dev = -1, n_sm = 0;   // static + dynamic shared memory can exceed 48 KB: opt in once
             int dev = -1;
             cudaGetDevice(&dev);
             if (dev != smem_dev) {
                 cudaFuncSetAttribute(k_stack_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxStageBytes);
+                cudaFuncSetAttribute(k_stack_ws, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     4 * kMaxStageBytes + kMaxLayers * 1024);
+                cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
                 smem_dev = dev;
             }
             PT.stage_bytes = (stage + 127) & ~127;
-            PT.stages_log2 = 4 * PT.stage_bytes <= 36 * 1024 ? 2 : 1;   // keep 4 CTAs per SM resident
-            k_stack_opaque<<<grid, kFWarps * 32, PT.stage_bytes << PT.stages_log2, stream>>>(PT);
+            PT.stages_log2 = 4 * PT.stage_bytes <= 36 * 1024 ? 2 : 1;   // keep 3-4 CTAs per SM resident
+            static const bool tile_kernel = [] {   // diagnostics: MVB_STACK_KERNEL=tile selects the one-CTA-per-tile form
+                const char* e = std::getenv("MVB_STACK_KERNEL");
+                return e && std::string(e) == "tile";
+            }();
+            if (tile_kernel) {
+                k_stack_opaque<<<grid, kFWarps * 32, PT.stage_bytes << PT.stages_log2, stream>>>(PT);
+            } else {
+                const int n_tiles = (int)(grid.x * grid.y);
+                const int ctas = n_tiles < 3 * n_sm ? n_tiles : 3 * n_sm;
+                k_stack_ws<<<ctas, kWsThreads, (PT.stage_bytes << PT.stages_log2) + n * 1024, stream>>>(PT);
+            }
         } else {
             k_composite_stack<false><<<grid, kWarps * 32, 0, stream>>>(P);
         }

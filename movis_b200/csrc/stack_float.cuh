@@ -254,6 +254,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         if (spins > (1u << 22)) __trap();
     }
 }
+// One non-blocking probe of the phase with the given parity.
+__device__ __forceinline__ int mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return (int)done;
+}
 // One box of the tiled tensor map -> shared memory; completion is signalled on `bar` (bytes).
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const void* map, int x, int y, uint32_t bar)
 {
@@ -268,6 +276,154 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 }
 
 enum { kTileTma = 3 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
+
+// What identifies a thread's pixels inside the tile being walked.
+struct PixelCtx {
+    int tx0, ty0;   // tile origin in the frame
+    int x;          // the thread's column
+    int rbeg;       // first of its kFRows rows, relative to ty0
+    int lane;
+    bool x_ok;      // x < frame width
+};
+
+// One layer of the walk for one thread: fetch the taps of its four rows (from the TMA-staged box,
+// or through L1 for layers that cannot be staged), cv2's fixed-point bilinear, opacity LUT, blend
+// into the pixels `d`.  `before_tma_wait(info)` runs ahead of the wait on the stage's barrier.
+template <class Slot, class BeforeTmaWait>
+__device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, int layer_index, const PixelCtx& C,
+                                           RowPairState (&d)[2], const uint32_t* softg, BeforeTmaWait&& before_tma_wait)
+{
+    const int tx0 = C.tx0, ty0 = C.ty0, x = C.x, rbeg = C.rbeg, lane = C.lane;
+    const bool x_ok = C.x_ok;
+    (void)tx0;
+    const int4 info = S.info;
+    const int cls = (info.x >> 8) & 3;
+    const bool part = info.x & (1 << 10);
+    const int2 col = S.col[lane];
+    const int2* __restrict__ rowtab = &S.row[rbeg];
+
+    // ---- taps of the four rows, all requested before the first is used ----------------------
+    uint32_t t[kFRows][4];
+    float fxs[kFRows];
+    uint32_t wy[kFRows];
+    unsigned ok = 0xFu;   // bit q: row q of this thread lies inside the layer's bbox and the frame
+    if (cls == kTileTma) {
+        before_tma_wait(info);
+        const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
+        if (part) {
+            const int4 bb = S.box;
+            const bool col_in = x_ok && (unsigned)(x - bb.x) < (unsigned)bb.z;
+            ok = 0;
+#pragma unroll
+            for (int q = 0; q < kFRows; ++q) {
+                const int yy = ty0 + rbeg + q;
+                ok |= (col_in && (unsigned)(yy - bb.y) < (unsigned)bb.w && yy < P.H) ? (1u << q) : 0u;
+            }
+        }
+        mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
+#pragma unroll
+        for (int q = 0; q < kFRows; ++q) {
+            const int2 r = rowtab[q];
+            const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
+            uint32_t a = stage + (uint32_t)(sumy >> 10) * pitch + (uint32_t)(sumx >> 10) * 4u;
+            if (part) a = (ok >> q & 1) ? a : stage;               // outside the bbox: any valid address; alpha is zeroed below
+            t[q][0] = lds_u32(a);
+            t[q][1] = lds_u32(a + 4);
+            t[q][2] = lds_u32(a + pitch);
+            t[q][3] = lds_u32(a + pitch + 4);
+            fxs[q] = (float)(sumx & 0x3E0);                        // 32 * fx
+            wy[q] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;     // bytes (32 - fy, fy, 0, 0)
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive((uint32_t)info.y + 32);         // this warp is done with the stage
+    } else if (cls == kTileInterior) {
+        const DevLayer& L = P.layers[layer_index];
+        const uint8_t* __restrict__ src = L.src;
+        const int ss = L.src_stride;
+#pragma unroll
+        for (int k = 0; k < kFRows; ++k) {
+            const int2 r = rowtab[k];
+            const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px (cv2: X0 + adelta)
+            const uint8_t* p = src + ((uint32_t)(sumy >> 10) * (uint32_t)ss + (uint32_t)(sumx >> 10) * 4u);
+            t[k][0] = ldg_u32(p);
+            t[k][1] = ldg_u32(p + 4);
+            t[k][2] = ldg_u32(p + ss);
+            t[k][3] = ldg_u32(p + ss + 4);
+            fxs[k] = (float)(sumx & 0x3E0);
+            wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
+        }
+    } else {
+        const DevLayer& L = P.layers[layer_index];
+        const uint8_t* __restrict__ src = L.src;
+        const int ss = L.src_stride;
+        const int sw = L.src_w, sh = L.src_h;
+        const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
+#pragma unroll
+        for (int k = 0; k < kFRows; ++k) {
+            const int2 r = rowtab[k];
+            const int sumx = r.x + col.x, sumy = r.y + col.y;
+            const int yy = ty0 + rbeg + k;
+            t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0u;
+            if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) {
+                const Taps tp = fetch_taps(src, sw, sh, ss, sumx >> 5, sumy >> 5);
+                t[k][0] = tp.p00; t[k][1] = tp.p01; t[k][2] = tp.p10; t[k][3] = tp.p11;
+            }
+            fxs[k] = (float)(sumx & 0x3E0);
+            wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
+        }
+    }
+
+    // ---- cv2's fixed-point bilinear: out = (sum w p + 512) >> 10 -------------------------------
+    u64 s[2][4], fa[2];
+    // &lut[bits - kMagicBits] for the biased alpha `bits`: one LEA (the shift drops the exponent bits)
+    const uint32_t lut_base = (uint32_t)info.z;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        float vl[2][4], vr[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = 2 * p + q;
+            const uint32_t wa = wy[k], wb = wy[k] << 16;
+            const uint32_t l_rg = __byte_perm(t[k][0], t[k][2], 0x5140), l_ba = __byte_perm(t[k][0], t[k][2], 0x7362);
+            const uint32_t r_rg = __byte_perm(t[k][1], t[k][3], 0x5140), r_ba = __byte_perm(t[k][1], t[k][3], 0x7362);
+            vl[q][0] = __uint_as_float(__dp4a(l_rg, wa, kTwo23Bits));   // 2^23 + p00 (32 - fy) + p10 fy
+            vl[q][1] = __uint_as_float(__dp4a(l_rg, wb, kTwo23Bits));
+            vl[q][2] = __uint_as_float(__dp4a(l_ba, wa, kTwo23Bits));
+            vl[q][3] = __uint_as_float(__dp4a(l_ba, wb, kTwo23Bits));
+            vr[q][0] = __uint_as_float(__dp4a(r_rg, wa, kTwo23Bits));
+            vr[q][1] = __uint_as_float(__dp4a(r_rg, wb, kTwo23Bits));
+            vr[q][2] = __uint_as_float(__dp4a(r_ba, wa, kTwo23Bits));
+            vr[q][3] = __uint_as_float(__dp4a(r_ba, wb, kTwo23Bits));
+        }
+        const u64 fx2 = pk(fxs[2 * p], fxs[2 * p + 1]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            // 32 (32 vl + fx (vr - vl) + 512) = 1024 vl + (32 fx)(vr - vl) + 16384  < 2^24
+            const u64 vl2 = pk(vl[0][c], vl[1][c]);
+            const u64 dd = sub2(pk(vr[0][c], vr[1][c]), vl2);
+            const u64 tt = fma2(vl2, bc(1024.0f), bc(16384.0f - 8589934592.0f));
+            s[p][c] = fma2_rm(fma2(fx2, dd, tt), bc(1.0f / 32768.0f), bc(kMagic));
+        }
+        float a0, a1;
+        upk(s[p][3], a0, a1);
+        uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);
+        if (part) {   // rows outside the bbox sampled a dummy address: alpha 0 -> lut[0] = 0 -> no-op
+            i0 = (ok >> (2 * p) & 1) ? i0 : kMagicBits;
+            i1 = (ok >> (2 * p + 1) & 1) ? i1 : kMagicBits;
+        }
+        fa[p] = pk(lds_f32(lut_base + (i0 << 2)), lds_f32(lut_base + (i1 << 2)));
+    }
+
+    // ---- blend, in the code specialised for this layer's mode ------------------------------------
+    switch (info.x & 255) {
+#define MVB_ROWS(M) case M: blend_rows<M>(d, s, fa, softg); break;
+        MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
+        MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
+        MVB_ROWS(15) MVB_ROWS(16) MVB_ROWS(17) MVB_ROWS(18)
+#undef MVB_ROWS
+    default: break;
+    }
+}
 
 // Position of the n-th (0-based) set bit of `mask` (n below its popcount, n small).
 __device__ __forceinline__ int nth_set_bit(unsigned mask, int n)
@@ -359,6 +515,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
     const int x = tx0 + lane;
     const int rbeg = warp * kFRows;
     const bool x_ok = x < P.W;
+    const PixelCtx px{tx0, ty0, x, rbeg, lane, x_ok};
     RowPairState d[2];
     if (P.keep_frame) {   // continuing a stack of more than kMaxLayers layers: alpha is 255 already
         uint32_t v[kFRows];
@@ -441,138 +598,13 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
 
 #pragma unroll 1
         for (int slot = 0; slot < n_here; ++slot) {
-            const SlotMem& S = s_slot[slot];
-            const int4 info = S.info;
-            const int cls = (info.x >> 8) & 3;
-            const bool part = info.x & (1 << 10);
-            const int2 col = S.col[lane];
-            const int2* __restrict__ rowtab = &S.row[rbeg];
-
-            // ---- taps of the four rows, all requested before the first is used ----------------------
-            uint32_t t[kFRows][4];
-            float fxs[kFRows];
-            uint32_t wy[kFRows];
-            unsigned ok = 0xFu;   // bit q: row q of this thread lies inside the layer's bbox and the frame
-            if (cls == kTileTma) {
+            walk_layer(P, s_slot[slot], s_layer[slot] & 255, px, d, s_softg, [&](const int4& info) {
                 if (tid == 0 && (info.x & (1 << 12))) {   // the stage of layer k-1 is free once every warp has read it
                     const int k = s_layer[slot] >> 8;
                     mbar_wait(bar_empty + 8 * ((k - 1) & ns_mask), ((k - 1) >> ns_log2) & 1);
                     request(k + ns_mask);
                 }
-                const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
-                if (part) {
-                    const int4 bb = S.box;
-                    const bool col_in = x_ok && (unsigned)(x - bb.x) < (unsigned)bb.z;
-                    ok = 0;
-#pragma unroll
-                    for (int q = 0; q < kFRows; ++q) {
-                        const int yy = ty0 + rbeg + q;
-                        ok |= (col_in && (unsigned)(yy - bb.y) < (unsigned)bb.w && yy < P.H) ? (1u << q) : 0u;
-                    }
-                }
-                mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
-#pragma unroll
-                for (int q = 0; q < kFRows; ++q) {
-                    const int2 r = rowtab[q];
-                    const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
-                    uint32_t a = stage + (uint32_t)(sumy >> 10) * pitch + (uint32_t)(sumx >> 10) * 4u;
-                    if (part) a = (ok >> q & 1) ? a : stage;               // outside the bbox: any valid address; alpha is zeroed below
-                    t[q][0] = lds_u32(a);
-                    t[q][1] = lds_u32(a + 4);
-                    t[q][2] = lds_u32(a + pitch);
-                    t[q][3] = lds_u32(a + pitch + 4);
-                    fxs[q] = (float)(sumx & 0x3E0);                        // 32 * fx
-                    wy[q] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;     // bytes (32 - fy, fy, 0, 0)
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive((uint32_t)info.y + 32);         // this warp is done with the stage
-            } else if (cls == kTileInterior) {
-                const DevLayer& L = P.layers[s_layer[slot] & 255];
-                const uint8_t* __restrict__ src = L.src;
-                const int ss = L.src_stride;
-#pragma unroll
-                for (int k = 0; k < kFRows; ++k) {
-                    const int2 r = rowtab[k];
-                    const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px (cv2: X0 + adelta)
-                    const uint8_t* p = src + ((uint32_t)(sumy >> 10) * (uint32_t)ss + (uint32_t)(sumx >> 10) * 4u);
-                    t[k][0] = ldg_u32(p);
-                    t[k][1] = ldg_u32(p + 4);
-                    t[k][2] = ldg_u32(p + ss);
-                    t[k][3] = ldg_u32(p + ss + 4);
-                    fxs[k] = (float)(sumx & 0x3E0);
-                    wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
-                }
-            } else {
-                const DevLayer& L = P.layers[s_layer[slot] & 255];
-                const uint8_t* __restrict__ src = L.src;
-                const int ss = L.src_stride;
-                const int sw = L.src_w, sh = L.src_h;
-                const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
-#pragma unroll
-                for (int k = 0; k < kFRows; ++k) {
-                    const int2 r = rowtab[k];
-                    const int sumx = r.x + col.x, sumy = r.y + col.y;
-                    const int yy = ty0 + rbeg + k;
-                    t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0u;
-                    if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) {
-                        const Taps tp = fetch_taps(src, sw, sh, ss, sumx >> 5, sumy >> 5);
-                        t[k][0] = tp.p00; t[k][1] = tp.p01; t[k][2] = tp.p10; t[k][3] = tp.p11;
-                    }
-                    fxs[k] = (float)(sumx & 0x3E0);
-                    wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
-                }
-            }
-
-            // ---- cv2's fixed-point bilinear: out = (sum w p + 512) >> 10 -------------------------------
-            u64 s[2][4], fa[2];
-            // &lut[bits - kMagicBits] for the biased alpha `bits`: one LEA (the shift drops the exponent bits)
-            const uint32_t lut_base = (uint32_t)info.z;
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                float vl[2][4], vr[2][4];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int k = 2 * p + q;
-                    const uint32_t wa = wy[k], wb = wy[k] << 16;
-                    const uint32_t l_rg = __byte_perm(t[k][0], t[k][2], 0x5140), l_ba = __byte_perm(t[k][0], t[k][2], 0x7362);
-                    const uint32_t r_rg = __byte_perm(t[k][1], t[k][3], 0x5140), r_ba = __byte_perm(t[k][1], t[k][3], 0x7362);
-                    vl[q][0] = __uint_as_float(__dp4a(l_rg, wa, kTwo23Bits));   // 2^23 + p00 (32 - fy) + p10 fy
-                    vl[q][1] = __uint_as_float(__dp4a(l_rg, wb, kTwo23Bits));
-                    vl[q][2] = __uint_as_float(__dp4a(l_ba, wa, kTwo23Bits));
-                    vl[q][3] = __uint_as_float(__dp4a(l_ba, wb, kTwo23Bits));
-                    vr[q][0] = __uint_as_float(__dp4a(r_rg, wa, kTwo23Bits));
-                    vr[q][1] = __uint_as_float(__dp4a(r_rg, wb, kTwo23Bits));
-                    vr[q][2] = __uint_as_float(__dp4a(r_ba, wa, kTwo23Bits));
-                    vr[q][3] = __uint_as_float(__dp4a(r_ba, wb, kTwo23Bits));
-                }
-                const u64 fx2 = pk(fxs[2 * p], fxs[2 * p + 1]);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    // 32 (32 vl + fx (vr - vl) + 512) = 1024 vl + (32 fx)(vr - vl) + 16384  < 2^24
-                    const u64 vl2 = pk(vl[0][c], vl[1][c]);
-                    const u64 dd = sub2(pk(vr[0][c], vr[1][c]), vl2);
-                    const u64 tt = fma2(vl2, bc(1024.0f), bc(16384.0f - 8589934592.0f));
-                    s[p][c] = fma2_rm(fma2(fx2, dd, tt), bc(1.0f / 32768.0f), bc(kMagic));
-                }
-                float a0, a1;
-                upk(s[p][3], a0, a1);
-                uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);
-                if (part) {   // rows outside the bbox sampled a dummy address: alpha 0 -> lut[0] = 0 -> no-op
-                    i0 = (ok >> (2 * p) & 1) ? i0 : kMagicBits;
-                    i1 = (ok >> (2 * p + 1) & 1) ? i1 : kMagicBits;
-                }
-                fa[p] = pk(lds_f32(lut_base + (i0 << 2)), lds_f32(lut_base + (i1 << 2)));
-            }
-
-            // ---- blend, in the code specialised for this layer's mode ------------------------------------
-            switch (info.x & 255) {
-#define MVB_ROWS(M) case M: blend_rows<M>(d, s, fa, s_softg); break;
-                MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
-                MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
-                MVB_ROWS(15) MVB_ROWS(16) MVB_ROWS(17) MVB_ROWS(18)
-#undef MVB_ROWS
-            default: break;
-            }
+            });
         }
     }
 

@@ -1,0 +1,262 @@
+// stack_ws.cuh -- persistent, warp-specialised form of the opaque-frame stack kernel (sm_100a).
+//
+// Same arithmetic as k_stack_opaque (stack_float.cuh: walk_layer) and the same contract: the frame
+// walk of Composition.__call__ (movis/layer/composition.py:363-368) with cv2.warpAffine ->
+// alpha_composite per layer (composition.py:811-819), bit for bit.  What changes is who does the
+// per-tile bookkeeping.  In k_stack_opaque all eight warps of a tile stop at two barriers while
+// warp 0 culls the layer list and the OpenCV tables are built; here every CTA is persistent
+// (grid = a few CTAs per SM, tiles taken round-robin) and has a ninth, PRODUCER warp that runs one
+// or two tiles ahead of the eight CONSUMER warps:
+//
+//   producer   cull + classify the layers against the next tile, build cv2's integer tables and the
+//              opacity LUT for up to 8 layers ("unit") into one of two shared-memory unit buffers,
+//              publish the unit (mbarrier), then request the layers' source boxes through TMA into
+//              a ring of stages as they become free;
+//   consumers  wait for the unit, walk its layers (taps from the TMA stages, float arithmetic,
+//              pixels in registers), release the unit, store the tile after its last unit.
+//
+// There is no __syncthreads() after start-up: all hand-offs are mbarrier phases, and the waits
+// are bounded (a wait that cannot complete traps instead of hanging the device).
+#pragma once
+
+#include "stack_float.cuh"
+
+namespace mvb {
+
+constexpr int kWsConsumers = kFWarps;             // 8 warps x 4 rows = one 32 x 32 tile
+constexpr int kWsThreads = (kWsConsumers + 1) * 32;
+constexpr int kWsSlots = 8;                       // layers per unit
+constexpr int kWsUnits = 2;                       // unit buffers: how far the producer may run ahead (power of two)
+
+// Per layer of a unit: as SlotMem, without the alpha LUT (one per layer per CTA here, see s_lut).
+struct __align__(16) UnitSlot {
+    int4 info;
+    int4 box;
+    int2 col[kTileW];
+    int2 row[kFTileH];
+};
+
+struct __align__(16) UnitMem {
+    int4 hdr;                 // x: tile x0, y: tile y0, z: layers in this unit | first << 8 | last << 9 | stop << 10
+    int layer[kWsSlots];      // layer index of each slot (for the layers that gather through L1)
+    UnitSlot slot[kWsSlots];
+};
+
+__global__ void __launch_bounds__(kWsThreads, 3)
+k_stack_ws(const __grid_constant__ StackParamsTma PT)
+{
+    const StackParams& P = PT.s;
+    extern __shared__ __align__(1024) uint8_t s_stage[];   // 2 or 4 stages of PT.stage_bytes, then the alpha LUTs
+    __shared__ UnitMem s_unit[kWsUnits];
+    __shared__ uint32_t s_softg[256];
+    __shared__ int32_t s_cull[kMaxLayers][17];             // first 64 bytes of every DevLayer (17: conflict-free by lane)
+    __shared__ __align__(8) unsigned long long s_bar[8 + 2 * kWsUnits];  // full[0..3], empty[0..3], unit_full[], unit_empty[]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[4]);
+    const uint32_t unit_full = smem_addr(&s_bar[8]), unit_empty = smem_addr(&s_bar[8 + kWsUnits]);
+    const uint32_t stage0 = smem_addr(s_stage);
+    const int ns_log2 = PT.stages_log2, ns_mask = (1 << ns_log2) - 1;
+    // opacity-scaled alpha as float, 256 entries per layer: the same for every tile, so built once per CTA
+    float* const s_lut = reinterpret_cast<float*>(s_stage + ((size_t)PT.stage_bytes << ns_log2));
+    const int tiles_x = (P.W + kTileW - 1) / kTileW, tiles_y = (P.H + kFTileH - 1) / kFTileH;
+    const int n_tiles = tiles_x * tiles_y;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, kWsConsumers);
+        }
+#pragma unroll
+        for (int i = 0; i < kWsUnits; ++i) {
+            mbar_init(unit_full + 8 * i, 1);
+            mbar_init(unit_empty + 8 * i, kWsConsumers);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 256) s_softg[tid] = g_blend_tables.softg[tid];
+    // a constant-bank read with a different address in every lane is replayed per address: the producer's
+    // one-layer-per-lane cull reads its records from shared memory instead
+    for (int i = tid; i < P.n_layers * 16; i += kWsThreads)
+        s_cull[i >> 4][i & 15] = reinterpret_cast<const int32_t*>(&P.layers[i >> 4])[i & 15];
+    for (int i = tid; i < P.n_layers * 256; i += kWsThreads) {
+        const DevLayer& L = P.layers[i >> 8];
+        const int a = i & 255;
+        uint32_t v = (uint32_t)a;
+        if (L.opacity < 1.0)
+            v = L.pil ? (uint32_t)(a * L.pil_a) / 255u                          // imgproc.py:206-208
+                      : __double2uint_rz(__dmul_rn((double)a, L.opacity));      // imgproc.py:159
+        s_lut[i] = (float)v;
+    }
+    __syncthreads();
+
+    if (warp == kWsConsumers) {
+        // =========================== producer warp ===============================================
+        int u = 0;   // units published so far
+        int g = 0;   // TMA boxes requested so far (position in the stage ring)
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int tx0 = (t % tiles_x) * kTileW, ty0 = (t / tiles_x) * kFTileH;
+            // ---- cull + classify: one layer per lane (as in k_stack_opaque) -------------------------
+            int cls = -1;
+            int2 org = make_int2(0, 0);
+            if (lane < P.n_layers) {
+                const int32_t* C = s_cull[lane];
+                const int bx = C[0], by = C[1], bw = C[2], bh = C[3], src_w = C[4], src_h = C[5], box_w = C[6], box_h = C[7];
+                const float m0 = __int_as_float(C[8]), m1 = __int_as_float(C[9]), m2 = __int_as_float(C[10]);
+                const float m3 = __int_as_float(C[11]), m4 = __int_as_float(C[12]), m5 = __int_as_float(C[13]);
+                const int u0 = max(tx0, bx) - bx, u1 = min(min(tx0 + kTileW, bx + bw), P.W) - 1 - bx;
+                const int v0 = max(ty0, by) - by, v1 = min(min(ty0 + kFTileH, by + bh), P.H) - 1 - by;
+                if (bw > 0 && bh > 0 && u0 <= u1 && v0 <= v1) {
+                    const float uc = 0.5f * (float)(u0 + u1), vc = 0.5f * (float)(v0 + v1);
+                    const float hu = 0.5f * (float)(u1 - u0), hv = 0.5f * (float)(v1 - v0);
+                    const float xc = m0 * uc + m1 * vc + m2, ex = fabsf(m0) * hu + fabsf(m1) * hv;
+                    const float yc = m3 * uc + m4 * vc + m5, ey = fabsf(m3) * hu + fabsf(m4) * hv;
+                    const float xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
+                    const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == kFTileH - 1;
+                    if (!(xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f)) {
+                        cls = kTileEdge;
+                        const int fx0 = ((int)floorf(xmin) - 1) & ~3, fy0 = (int)floorf(ymin) - 1;
+                        if (box_w > 0 && (int)floorf(xmax) + 3 - fx0 <= box_w && (int)floorf(ymax) + 3 - fy0 <= box_h) {
+                            cls = kTileTma | (full ? 0 : 256);
+                            org = make_int2(fx0, fy0);
+                        } else if (full && xmin > 0.25f && xmax < src_w - 1.25f && ymin > 0.25f && ymax < src_h - 1.25f) {
+                            cls = kTileInterior;
+                        }
+                    }
+                }
+            }
+            unsigned rest = __ballot_sync(0xFFFFFFFFu, cls >= 0);   // active layers, paint order = bit order
+            bool first = true;
+            do {   // one unit per 8 active layers; a tile without layers still gets one (background only)
+                const int n_here = min(kWsSlots, __popc(rest));
+                // lane s < n_here owns slot s of the unit: its layer, class, box origin and ring position
+                int my_li = 0;
+                if (lane < n_here) my_li = nth_set_bit(rest, lane);
+                const int my_c = __shfl_sync(0xFFFFFFFFu, cls, my_li);
+                const int2 my_org = make_int2(__shfl_sync(0xFFFFFFFFu, org.x, my_li), __shfl_sync(0xFFFFFFFFu, org.y, my_li));
+                const unsigned want = __ballot_sync(0xFFFFFFFFu, lane < n_here && (my_c & 255) == kTileTma);
+                const int my_g = g + __popc(want & ((1u << lane) - 1u));
+                for (int i = 0; i < n_here; ++i) rest &= rest - 1;
+
+                // Request the boxes of the unit's TMA layers, in ring order, once the unit is published
+                // (probing for free stages before building the tables was measured slower).
+                unsigned todo = want;
+                auto request = [&](bool may_block) {
+                    while (todo) {
+                        const int s = __ffs((int)todo) - 1;
+                        const int li = __shfl_sync(0xFFFFFFFFu, my_li, s), gq = __shfl_sync(0xFFFFFFFFu, my_g, s);
+                        const int ox = __shfl_sync(0xFFFFFFFFu, my_org.x, s), oy = __shfl_sync(0xFFFFFFFFu, my_org.y, s);
+                        const int st = gq & ns_mask;
+                        int go = 1;
+                        if (lane == 0 && gq > ns_mask) {   // free once every consumer warp has read the previous box
+                            const uint32_t bar = bar_empty + 8 * st, parity = ((gq >> ns_log2) - 1) & 1;
+                            if (may_block) mbar_wait(bar, parity);
+                            else go = mbar_test(bar, parity);
+                        }
+                        go = __shfl_sync(0xFFFFFFFFu, go, 0);
+                        if (!go) break;
+                        if (lane == 0) {
+                            const DevLayer& L = P.layers[li];
+                            mbar_arrive_expect_tx(bar_full + 8 * st, (uint32_t)(L.box_w * L.box_h * 4));
+                            tma_load_box(stage0 + st * PT.stage_bytes, &PT.maps[li], ox, oy, bar_full + 8 * st);
+                        }
+                        __syncwarp();
+                        todo &= todo - 1;
+                    }
+                };
+
+                UnitMem& U = s_unit[u & (kWsUnits - 1)];
+                if (u >= kWsUnits)   // consumers are done with this buffer
+                    mbar_wait(unit_empty + 8 * (u & (kWsUnits - 1)), ((u / kWsUnits) - 1) & 1);
+                for (int slot = 0; slot < n_here; ++slot) {
+                    const int li = __shfl_sync(0xFFFFFFFFu, my_li, slot), c = __shfl_sync(0xFFFFFFFFu, my_c, slot);
+                    const int ox = __shfl_sync(0xFFFFFFFFu, my_org.x, slot), oy = __shfl_sync(0xFFFFFFFFu, my_org.y, slot);
+                    const int gq = __shfl_sync(0xFFFFFFFFu, my_g, slot);
+                    const DevLayer& L = P.layers[li];
+                    UnitSlot& S = U.slot[slot];
+                    // cv::warpAffine's tables restricted to the tile: lane = column, then lane = row
+                    S.col[lane] = make_int2(warp_adelta(L.m, tx0 + lane - L.bx), warp_bdelta(L.m, tx0 + lane - L.bx));
+                    S.row[lane] = make_int2(warp_x0(L.m, ty0 + lane - L.by) - ox * 1024, warp_y0(L.m, ty0 + lane - L.by) - oy * 1024);
+                    if (lane == 0) {
+                        // x: mode (8 bits) | class (2) | partial coverage (bit 10) | phase parity (bit 11) | row pitch << 16
+                        // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]   w: stage address
+                        S.info = make_int4((L.pil ? kPilOver : L.mode) | ((c & 3) << 8) | ((c >> 8) << 10) |
+                                               (((gq >> ns_log2) & 1) << 11) | ((L.box_w * 4) << 16),
+                                           (int)(bar_full + 8 * (gq & ns_mask)),
+                                           (int)(smem_addr(s_lut + li * 256) - (kMagicBits << 2)),
+                                           (int)(stage0 + (gq & ns_mask) * PT.stage_bytes));
+                        S.box = make_int4(L.bx, L.by, L.bw, L.bh);
+                        U.layer[slot] = li;
+                    }
+                }
+                const bool last = rest == 0;
+                if (lane == 0) U.hdr = make_int4(tx0, ty0, n_here | (first ? 256 : 0) | (last ? 512 : 0), 0);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(unit_full + 8 * (u & (kWsUnits - 1)));   // publish (release: the warp's writes above)
+                request(true);
+                g += __popc(want);
+                ++u;
+                first = false;
+            } while (rest);
+        }
+        // ---- stop unit --------------------------------------------------------------------------------
+        if (u >= kWsUnits) mbar_wait(unit_empty + 8 * (u & (kWsUnits - 1)), ((u / kWsUnits) - 1) & 1);
+        if (lane == 0) {
+            s_unit[u & (kWsUnits - 1)].hdr = make_int4(0, 0, 1 << 10, 0);
+            mbar_arrive(unit_full + 8 * (u & (kWsUnits - 1)));
+        }
+    } else {
+        // =========================== consumer warps ==============================================
+        RowPairState d[2];
+        for (int u = 0;; ++u) {
+            const UnitMem& U = s_unit[u & (kWsUnits - 1)];
+            mbar_wait(unit_full + 8 * (u & (kWsUnits - 1)), (u / kWsUnits) & 1);
+            const int4 hdr = U.hdr;
+            if (hdr.z & (1 << 10)) break;
+            const int tx0 = hdr.x, ty0 = hdr.y, n_here = hdr.z & 255;
+            const int x = tx0 + lane, rbeg = warp * kFRows;
+            const bool x_ok = x < P.W;
+            const PixelCtx px{tx0, ty0, x, rbeg, lane, x_ok};
+            if (hdr.z & 256) {   // first unit of the tile: background
+                if (P.keep_frame) {   // continuing a stack of more than kMaxLayers layers: alpha is 255 already
+                    uint32_t v[kFRows];
+#pragma unroll
+                    for (int k = 0; k < kFRows; ++k)   // clamped, not predicated; out-of-frame threads never store
+                        v[k] = reinterpret_cast<const uint32_t*>(P.frame + (int64_t)min(ty0 + rbeg + k, P.H - 1) * P.stride)[min(x, P.W - 1)];
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            d[p].c[c] = pk(__uint_as_float(__byte_perm(v[2 * p], kMagicBits, 0x7650 + c)),
+                                           __uint_as_float(__byte_perm(v[2 * p + 1], kMagicBits, 0x7650 + c)));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d[0].c[c] = d[1].c[c] = bc(kMagic + (float)((P.bg >> (8 * c)) & 0xFFu));
+                }
+            }
+#pragma unroll 1
+            for (int slot = 0; slot < n_here; ++slot)
+                walk_layer(P, U.slot[slot], U.layer[slot], px, d, s_softg, [](const int4&) {});
+            __syncwarp();
+            if (lane == 0) mbar_arrive(unit_empty + 8 * (u & (kWsUnits - 1)));   // this warp no longer reads the unit
+            if ((hdr.z & 512) && x_ok) {   // last unit of the tile: one coalesced 128-byte store per warp row
+#pragma unroll
+                for (int k = 0; k < kFRows; ++k) {
+                    if (ty0 + rbeg + k >= P.H) break;
+                    float r0, r1, g0, g1, b0, b1;
+                    upk(d[k >> 1].c[0], r0, r1);
+                    upk(d[k >> 1].c[1], g0, g1);
+                    upk(d[k >> 1].c[2], b0, b1);
+                    const uint32_t rb = __float_as_uint((k & 1) ? r1 : r0), gb = __float_as_uint((k & 1) ? g1 : g0);
+                    const uint32_t bb = __float_as_uint((k & 1) ? b1 : b0);
+                    const uint32_t pxl = __byte_perm(__byte_perm(rb, gb, 0x0040), bb, 0x0410) | 0xFF000000u;
+                    reinterpret_cast<uint32_t*>(P.frame + (int64_t)(ty0 + rbeg + k) * P.stride)[x] = pxl;
+                }
+            }
+        }
+    }
+}
+
+} // namespace mvb
