@@ -26,7 +26,7 @@ namespace mvb {
 constexpr int kWsConsumers = kFWarps;             // 8 warps x 4 rows = one 32 x 32 tile
 constexpr int kWsThreads = (kWsConsumers + 1) * 32;
 constexpr int kWsSlots = 8;                       // layers per unit
-constexpr int kWsUnits = 2;                       // unit buffers: how far the producer may run ahead (power of two)
+constexpr int kWsUnits = 4;                       // unit buffers: how far the producer may run ahead (power of two)
 
 // Per layer of a unit: as SlotMem, without the alpha LUT (one per layer per CTA here, see s_lut).
 struct __align__(16) UnitSlot {
@@ -95,7 +95,42 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
     if (warp == kWsConsumers) {
         // =========================== producer warp ===============================================
         int u = 0;   // units published so far
-        int g = 0;   // TMA boxes requested so far (position in the stage ring)
+        int g = 0;   // TMA boxes assigned so far (position in the stage ring)
+        // Boxes assigned but not yet requested, because their stage was still being read: request number
+        // q waits in lane q & 31 (at most 4 units x 8 layers are ever outstanding).  They are requested
+        // in order, whenever the producer passes by and the stage has come free -- never blocking the
+        // building of the next unit, which is what the consumers run out of first.
+        int head = 0;   // next request number to issue
+        int q_li = 0, q_ox = 0, q_oy = 0;
+        auto service = [&]() {
+            while (head < g) {
+                const int st = head & ns_mask;
+                int go = 1;
+                if (lane == 0 && head > ns_mask) go = mbar_test(bar_empty + 8 * st, ((head >> ns_log2) - 1) & 1);
+                go = __shfl_sync(0xFFFFFFFFu, go, 0);
+                if (!go) break;
+                const int li = __shfl_sync(0xFFFFFFFFu, q_li, head & 31);
+                const int ox = __shfl_sync(0xFFFFFFFFu, q_ox, head & 31), oy = __shfl_sync(0xFFFFFFFFu, q_oy, head & 31);
+                if (lane == 0) {
+                    const DevLayer& L = P.layers[li];
+                    mbar_arrive_expect_tx(bar_full + 8 * st, (uint32_t)(L.box_w * L.box_h * 4));
+                    tma_load_box(stage0 + st * PT.stage_bytes, &PT.maps[li], ox, oy, bar_full + 8 * st);
+                }
+                __syncwarp();
+                ++head;
+            }
+        };
+        // Wait for a phase while keeping the request queue moving (the consumers may need those boxes
+        // to get to the arrival this wait is for).
+        auto wait_servicing = [&](uint32_t bar, uint32_t parity) {
+            for (uint32_t spins = 0;; ++spins) {
+                int done = 0;
+                if (lane == 0) done = mbar_test(bar, parity);
+                if (__shfl_sync(0xFFFFFFFFu, done, 0)) return;
+                service();
+                if (spins > (1u << 24)) __trap();
+            }
+        };
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int tx0 = (t % tiles_x) * kTileW, ty0 = (t / tiles_x) * kFTileH;
             // ---- cull + classify: one layer per lane (as in k_stack_opaque) -------------------------
@@ -140,36 +175,18 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                 const int my_g = g + __popc(want & ((1u << lane) - 1u));
                 for (int i = 0; i < n_here; ++i) rest &= rest - 1;
 
-                // Request the boxes of the unit's TMA layers, in ring order, once the unit is published
-                // (probing for free stages before building the tables was measured slower).
-                unsigned todo = want;
-                auto request = [&](bool may_block) {
-                    while (todo) {
-                        const int s = __ffs((int)todo) - 1;
-                        const int li = __shfl_sync(0xFFFFFFFFu, my_li, s), gq = __shfl_sync(0xFFFFFFFFu, my_g, s);
-                        const int ox = __shfl_sync(0xFFFFFFFFu, my_org.x, s), oy = __shfl_sync(0xFFFFFFFFu, my_org.y, s);
-                        const int st = gq & ns_mask;
-                        int go = 1;
-                        if (lane == 0 && gq > ns_mask) {   // free once every consumer warp has read the previous box
-                            const uint32_t bar = bar_empty + 8 * st, parity = ((gq >> ns_log2) - 1) & 1;
-                            if (may_block) mbar_wait(bar, parity);
-                            else go = mbar_test(bar, parity);
-                        }
-                        go = __shfl_sync(0xFFFFFFFFu, go, 0);
-                        if (!go) break;
-                        if (lane == 0) {
-                            const DevLayer& L = P.layers[li];
-                            mbar_arrive_expect_tx(bar_full + 8 * st, (uint32_t)(L.box_w * L.box_h * 4));
-                            tma_load_box(stage0 + st * PT.stage_bytes, &PT.maps[li], ox, oy, bar_full + 8 * st);
-                        }
-                        __syncwarp();
-                        todo &= todo - 1;
-                    }
-                };
-
                 UnitMem& U = s_unit[u & (kWsUnits - 1)];
                 if (u >= kWsUnits)   // consumers are done with this buffer
-                    mbar_wait(unit_empty + 8 * (u & (kWsUnits - 1)), ((u / kWsUnits) - 1) & 1);
+                    wait_servicing(unit_empty + 8 * (u & (kWsUnits - 1)), ((u / kWsUnits) - 1) & 1);
+                // queue the unit's TMA requests (slot order = ring order)
+                for (unsigned w = want; w; w &= w - 1) {
+                    const int sl = __ffs((int)w) - 1;
+                    const int gq = __shfl_sync(0xFFFFFFFFu, my_g, sl), li = __shfl_sync(0xFFFFFFFFu, my_li, sl);
+                    const int ox = __shfl_sync(0xFFFFFFFFu, my_org.x, sl), oy = __shfl_sync(0xFFFFFFFFu, my_org.y, sl);
+                    if (lane == (gq & 31)) { q_li = li; q_ox = ox; q_oy = oy; }
+                }
+                g += __popc(want);
+                service();
                 for (int slot = 0; slot < n_here; ++slot) {
                     const int li = __shfl_sync(0xFFFFFFFFu, my_li, slot), c = __shfl_sync(0xFFFFFFFFu, my_c, slot);
                     const int ox = __shfl_sync(0xFFFFFFFFu, my_org.x, slot), oy = __shfl_sync(0xFFFFFFFFu, my_org.y, slot);
@@ -195,17 +212,20 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                 if (lane == 0) U.hdr = make_int4(tx0, ty0, n_here | (first ? 256 : 0) | (last ? 512 : 0), 0);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(unit_full + 8 * (u & (kWsUnits - 1)));   // publish (release: the warp's writes above)
-                request(true);
-                g += __popc(want);
+                service();
                 ++u;
                 first = false;
             } while (rest);
         }
         // ---- stop unit --------------------------------------------------------------------------------
-        if (u >= kWsUnits) mbar_wait(unit_empty + 8 * (u & (kWsUnits - 1)), ((u / kWsUnits) - 1) & 1);
+        if (u >= kWsUnits) wait_servicing(unit_empty + 8 * (u & (kWsUnits - 1)), ((u / kWsUnits) - 1) & 1);
         if (lane == 0) {
             s_unit[u & (kWsUnits - 1)].hdr = make_int4(0, 0, 1 << 10, 0);
             mbar_arrive(unit_full + 8 * (u & (kWsUnits - 1)));
+        }
+        for (uint32_t spins = 0; head < g; ++spins) {   // the boxes the consumers are still waiting for
+            service();
+            if (spins > (1u << 24)) __trap();
         }
     } else {
         // =========================== consumer warps ==============================================
