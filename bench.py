@@ -12,8 +12,9 @@ frame.  Metric: composited frames/sec (whole job, all GPUs).
   value     frames/s with sources resident in HBM and frames left in HBM (device timed, CUDA events)
   e2e       frames/s through the public API with HOST buffers: every step uploads the 16 sources
             from pinned host memory and delivers every finished uint8 frame to pinned host memory
-  roofline  achieved algorithmic GB/s of the fused kernel (B_frame = 4*W*H + sum 4*w_l*h_l =
-            165 888 000 B, each source texel and each output pixel counted once) / measured HBM peak
+  roofline  achieved algorithmic GB/s of the fused kernel k_stack_ws (B_frame = 4*W*H + sum 4*w_l*h_l =
+            165 888 000 B, each source texel and each output pixel counted once) / measured HBM peak;
+            `traffic` = dram bytes per launch from the committed ncu capture (profiles/roofline_traffic.json)
   cpu_baseline  the CPU oracle (a C + OpenMP port of the reference algorithm) on the host cores
 
 Multi-GPU: launched with torchrun, one rank per GPU; each rank renders its own contiguous 150-frame
@@ -237,7 +238,7 @@ def run_product(args) -> dict:
     peak, peak_src = measured_hbm_peak()
     achieved = b_frame / launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(), "kernel": "k_composite_stack",
+                "traffic": recorded_traffic(), "kernel": "k_stack_ws",
                 "algorithmic_bytes_per_launch": b_frame, "avg_launch_us": launch_s * 1e6, "peak_source": peak_src}
 
     # --- e2e: host sources -> device, render, every frame back to pinned host memory ---------------
