@@ -11,7 +11,8 @@
  *   - Plain C types only.  Every image is uint8 RGBA, HWC, non-premultiplied, in DEVICE memory,
  *     described by (pointer, width, height, row stride in bytes).  Row strides must be multiples
  *     of 4 and pointers 4-byte aligned.  Source images must be smaller than 32768 px per side
- *     (cv2's own limit for warpAffine).
+ *     (cv2's own limit for warpAffine).  Layer sources whose pointer AND stride are multiples of 16
+ *     are staged through TMA by mvb_composite_stack; others are gathered through L1 (same results).
  *   - No ownership transfer and no hidden allocation: all buffers are caller-allocated.
  *   - Every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
  *     synchronising.  Small host-side parameter blocks (layer descriptors, LUTs, weights) are
