@@ -10,6 +10,7 @@
 //            (uint16 x C per pixel: sum w = 256 keeps it inside 16 bits)
 //   V pass:  out[Y][X] = (sum_i w[i] * mid[clamp(Y + i - r - k)][X] + 32768) >> 16
 //            (alpha rows outside the source contribute 0), with the Glow composite fused in.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -97,6 +98,173 @@ __global__ void __launch_bounds__(256) k_blur_v_rgba(const __grid_constant__ Blu
     reinterpret_cast<uint32_t*>(P.dst + (int64_t)Y * P.dstride)[X] = o;
 }
 
+// ---- tiled RGBA blur (k <= kTiledMaxK, every weight <= 255) ---------------------------------------
+// Same arithmetic as k_blur_h_rgba / k_blur_v_rgba; what changes is the data movement.
+//   H: a CTA stages one row segment (1024 outputs + k + 3 taps, padding rule applied once) in shared
+//      memory, transposed so that "thread t, tap j" is conflict-free; every thread produces 4
+//      adjacent outputs from a sliding window, two channels per IMAD (16-bit lanes: a Q8 weighted
+//      sum of bytes stays below 65 536), weights broadcast from shared memory.
+//   V: every thread produces 4 vertically adjacent outputs of one column, so each intermediate
+//      row is loaded once per 4 outputs (coalesced 8-byte loads); one IDP.2A per channel and tap
+//      (16-bit value x 8-bit weight, 32-bit accumulate).
+constexpr int kTiledMaxK = 255;
+constexpr int kBlurHOut = 1024;   // outputs per CTA of the H pass (4 per thread)
+
+__global__ void __launch_bounds__(256) k_blur_h_rgba_tiled(const __grid_constant__ BlurParams P)
+{
+    extern __shared__ uint32_t s_dyn[];
+    const int k = P.k, r = k >> 1, W2 = P.w + 2 * k;
+    const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);     // staged pixels (taps of the last output, rounded up)
+    const int Q = n_in >> 2;
+    uint32_t* s_px = s_dyn;                                // pixel i at (i & 3) * Q + (i >> 2)
+    uint32_t* s_w = s_dyn + n_in;                          // weight of tap jj at s_w[jj + 3]; zeros around
+    const int y = blockIdx.y, X0 = blockIdx.x * kBlurHOut;
+    const int t = threadIdx.x;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(P.src + (int64_t)y * P.sstride);
+    for (int i = t; i < n_in; i += 256) {
+        const int sx = X0 + i - r - k;                     // source x of staged pixel i (blur.py:39-40 padding)
+        uint32_t p = __ldg(row + min(max(sx, 0), P.w - 1));
+        if ((unsigned)sx >= (unsigned)P.w) p &= 0x00FFFFFFu;   // rgb edge-replicated, alpha zero-padded
+        s_px[(i & 3) * Q + (i >> 2)] = p;
+    }
+    for (int j = t; j < k + 12; j += 256) s_w[j] = (j >= 3 && j < k + 3) ? P.wt[j - 3] : 0u;
+    __syncthreads();
+    uint32_t rb[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0};
+    for (int j4 = 0; j4 * 4 < k + 3; ++j4) {
+        const uint4 wa = *reinterpret_cast<const uint4*>(s_w + 4 * j4);        // taps 4 j4 - 3 .. 4 j4
+        const uint4 wb = *reinterpret_cast<const uint4*>(s_w + 4 * j4 + 4);    // taps 4 j4 + 1 .. 4 j4 + 4
+        const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t p = s_px[jj * Q + t + j4];      // staged pixel 4 t + 4 j4 + jj
+            const uint32_t prb = p & 0x00FF00FFu, pga = (p >> 8) & 0x00FF00FFu;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {                  // output 4 t + m takes it as tap 4 j4 + jj - m
+                rb[m] += w[jj - m + 3] * prb;
+                ga[m] += w[jj - m + 3] * pga;
+            }
+        }
+    }
+    uint2* out = reinterpret_cast<uint2*>(P.mid) + (int64_t)y * W2;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int X = X0 + 4 * t + m;
+        if (X < W2) out[X] = make_uint2((rb[m] & 0xFFFFu) | (ga[m] << 16), (rb[m] >> 16) | (ga[m] & 0xFFFF0000u));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_blur_v_rgba_tiled(const __grid_constant__ BlurParams P)
+{
+    __shared__ uint2 s_w[kTiledMaxK + 9];                  // tap jj at s_w[jj + 3]: (w, w << 8) for the two dp2a halves
+    const int k = P.k, r = k >> 1;
+    const int W2 = P.w + 2 * k, H2 = P.h + 2 * k;
+    for (int j = threadIdx.x; j < k + 8; j += 256) {
+        const uint32_t w = (j >= 3 && j < k + 3) ? P.wt[j - 3] : 0u;
+        s_w[j] = make_uint2(w, w << 8);
+    }
+    __syncthreads();
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int Yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 4;
+    if (X >= W2 || Yb >= H2) return;
+    const uint2* mid = reinterpret_cast<const uint2*>(P.mid) + X;
+    uint32_t acc[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 32768u;   // rounding of (V + 32768) >> 16
+    const int y0 = Yb - r - k;
+    for (int j = 0; j < k + 3; ++j) {                      // intermediate row y0 + j is tap j - m of output Yb + m
+        const int sy = y0 + j;
+        uint2 v = __ldg(mid + (int64_t)min(max(sy, 0), P.h - 1) * W2);
+        if ((unsigned)sy >= (unsigned)P.h) v.y &= 0xFFFFu; // alpha zero-padded
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const uint2 w = s_w[j - m + 3];
+            acc[m][0] = __dp2a_lo(v.x, w.x, acc[m][0]);
+            acc[m][1] = __dp2a_lo(v.x, w.y, acc[m][1]);
+            acc[m][2] = __dp2a_lo(v.y, w.x, acc[m][2]);
+            acc[m][3] = __dp2a_lo(v.y, w.y, acc[m][3]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int Y = Yb + m;
+        if (Y >= H2) break;
+        Rgba s{acc[m][0] >> 16, acc[m][1] >> 16, acc[m][2] >> 16, acc[m][3] >> 16};
+        uint32_t o;
+        if (P.mode == MVB_BLUR_GLOW) {
+            const int sx = X - P.k, sy = Y - P.k;          // pad_image pixel (blur.py:74-76)
+            uint32_t d = __ldg(reinterpret_cast<const uint32_t*>(P.src + (int64_t)min(max(sy, 0), P.h - 1) * P.sstride) +
+                               min(max(sx, 0), P.w - 1));
+            if ((unsigned)sx >= (unsigned)P.w || (unsigned)sy >= (unsigned)P.h) d &= 0x00FFFFFFu;
+            s.r = P.lut[s.r]; s.g = P.lut[s.g]; s.b = P.lut[s.b]; // blur.py:82
+            o = over_numpy<MVB_BLEND_LINEAR_DODGE>(d, s, s.a, false); // blur.py:84-85
+        } else {
+            o = pack(s.r, s.g, s.b, s.a);
+        }
+        reinterpret_cast<uint32_t*>(P.dst + (int64_t)Y * P.dstride)[X] = o;
+    }
+}
+
+// Tiled H / V passes on the alpha channel only (DropShadow, style.py:60-62; zero padding): the same
+// staging and 4-outputs-per-thread sliding window as the RGBA kernels, one channel.
+__global__ void __launch_bounds__(256) k_blur_h_alpha_tiled(const __grid_constant__ BlurParams P)
+{
+    extern __shared__ uint32_t s_dyn[];
+    const int k = P.k, r = k >> 1, W2 = P.w + 2 * k;
+    const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);
+    const int Q = n_in >> 2;
+    uint32_t* s_px = s_dyn;
+    uint32_t* s_w = s_dyn + n_in;
+    const int y = blockIdx.y, X0 = blockIdx.x * kBlurHOut;
+    const int t = threadIdx.x;
+    const uint8_t* row = P.src + (int64_t)y * P.sstride + 3;
+    for (int i = t; i < n_in; i += 256) {
+        const int sx = X0 + i - r - k;
+        s_px[(i & 3) * Q + (i >> 2)] = (unsigned)sx < (unsigned)P.w ? row[(int64_t)sx * 4] : 0u;
+    }
+    for (int j = t; j < k + 12; j += 256) s_w[j] = (j >= 3 && j < k + 3) ? P.wt[j - 3] : 0u;
+    __syncthreads();
+    uint32_t a[4] = {0, 0, 0, 0};
+    for (int j4 = 0; j4 * 4 < k + 3; ++j4) {
+        const uint4 wa = *reinterpret_cast<const uint4*>(s_w + 4 * j4);
+        const uint4 wb = *reinterpret_cast<const uint4*>(s_w + 4 * j4 + 4);
+        const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t p = s_px[jj * Q + t + j4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) a[m] += w[jj - m + 3] * p;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int X = X0 + 4 * t + m;
+        if (X < W2) P.mid[(int64_t)y * W2 + X] = (uint16_t)a[m];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_blur_v_alpha_tiled(const __grid_constant__ BlurParams P)
+{
+    __shared__ uint32_t s_w[kTiledMaxK + 9];
+    const int k = P.k, r = k >> 1;
+    const int W2 = P.w + 2 * k, H2 = P.h + 2 * k;
+    for (int j = threadIdx.x; j < k + 8; j += 256) s_w[j] = (j >= 3 && j < k + 3) ? P.wt[j - 3] : 0u;
+    __syncthreads();
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int Yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 4;
+    if (X >= W2 || Yb >= H2) return;
+    uint32_t acc[4] = {32768u, 32768u, 32768u, 32768u};
+    const int y0 = Yb - r - k;
+    for (int j = 0; j < k + 3; ++j) {
+        const int sy = y0 + j;
+        const uint32_t v = (unsigned)sy < (unsigned)P.h ? P.mid[(int64_t)sy * W2 + X] : 0u;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[m] += s_w[j - m + 3] * v;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        if (Yb + m < H2) P.dst[(int64_t)(Yb + m) * P.dstride + X] = (uint8_t)(acc[m] >> 16);
+}
+
 // H / V passes on the alpha channel only (DropShadow, style.py:60-62): zero padding.
 __global__ void __launch_bounds__(256) k_blur_h_alpha(const __grid_constant__ BlurParams P)
 {
@@ -170,7 +338,7 @@ __global__ void __launch_bounds__(256) k_drop_shadow(const __grid_constant__ Sha
 // ---- colour conversions -----------------------------------------------------------------------
 
 struct HsvTables { int32_t sdiv[256]; int32_t hdiv[256]; };
-__constant__ HsvTables c_hsv;
+__device__ HsvTables g_hsv;   // global memory: every thread reads its own entry (a constant-bank read would replay per address)
 
 // cv2.COLOR_RGB2HSV, 8-bit, H in [0, 180)
 __device__ __forceinline__ void rgb_to_hsv(int r, int g, int b, const int32_t* sdiv, const int32_t* hdiv,
@@ -232,34 +400,57 @@ struct PointParams {
     uint8_t hlut[256], slut[256], vlut[256];
 };
 
+// One pixel of ChromaKey (op 0) / FillColor (op 1) / HSLShift (op 2).
+__device__ __forceinline__ uint32_t pointwise_px(const PointParams& P, uint32_t p, int x, const int32_t* sdiv,
+                                                 const int32_t* hdiv, const uint8_t* luts)
+{
+    if (P.op == 1) return P.color | (p & 0xFF000000u);
+    int hh, ss, vv;
+    rgb_to_hsv(p & 0xFF, (p >> 8) & 0xFF, (p >> 16) & 0xFF, sdiv, hdiv, hh, ss, vv);
+    if (P.op == 0) {
+        const bool in = hh >= P.lo[0] && hh <= P.hi[0] && ss >= P.lo[1] && ss <= P.hi[1] &&
+                        vv >= P.lo[2] && vv <= P.hi[2];
+        return (p & 0x00FFFFFFu) | (in ? 0u : 0xFF000000u);
+    }
+    const bool tail = x >= P.w - (P.w & 31);   // cv2 rounds instead of truncating in the scalar tail of a row
+    return hsv_to_rgb(luts[hh], luts[256 + ss], luts[512 + vv], tail) | (p & 0xFF000000u);
+}
+
+// Persistent grid-stride kernel: the tables are staged in shared memory once per CTA, pixels move
+// as 128-bit vectors (VEC = 4) when rows are 16-byte aligned.
+template <int VEC>
 __global__ void __launch_bounds__(256) k_pointwise(const __grid_constant__ PointParams P)
 {
     __shared__ int32_t s_sdiv[256], s_hdiv[256];
+    __shared__ uint8_t s_luts[768];
     if (P.op != 1) {
-        s_sdiv[threadIdx.x] = c_hsv.sdiv[threadIdx.x];
-        s_hdiv[threadIdx.x] = c_hsv.hdiv[threadIdx.x];
+        s_sdiv[threadIdx.x] = g_hsv.sdiv[threadIdx.x];
+        s_hdiv[threadIdx.x] = g_hsv.hdiv[threadIdx.x];
+        s_luts[threadIdx.x] = P.hlut[threadIdx.x];
+        s_luts[256 + threadIdx.x] = P.slut[threadIdx.x];
+        s_luts[512 + threadIdx.x] = P.vlut[threadIdx.x];
         __syncthreads();
     }
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= P.w || y >= P.h) return;
-    const uint32_t p = reinterpret_cast<const uint32_t*>(P.src + (int64_t)y * P.sstride)[x];
-    uint32_t o;
-    if (P.op == 1) {
-        o = P.color | (p & 0xFF000000u);
-    } else {
-        int hh, ss, vv;
-        rgb_to_hsv(p & 0xFF, (p >> 8) & 0xFF, (p >> 16) & 0xFF, s_sdiv, s_hdiv, hh, ss, vv);
-        if (P.op == 0) {
-            const bool in = hh >= P.lo[0] && hh <= P.hi[0] && ss >= P.lo[1] && ss <= P.hi[1] &&
-                            vv >= P.lo[2] && vv <= P.hi[2];
-            o = (p & 0x00FFFFFFu) | (in ? 0u : 0xFF000000u);
+    const int per_row = (P.w + VEC - 1) / VEC;
+    const long long total = (long long)per_row * P.h;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int y = (int)(i / per_row), x = (int)(i - (long long)y * per_row) * VEC;
+        const uint8_t* sp = P.src + (int64_t)y * P.sstride + (int64_t)x * 4;
+        uint8_t* dp = P.dst + (int64_t)y * P.dstride + (int64_t)x * 4;
+        if (VEC == 4 && x + 4 <= P.w) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sp);
+            uint4 o;
+            o.x = pointwise_px(P, v.x, x, s_sdiv, s_hdiv, s_luts);
+            o.y = pointwise_px(P, v.y, x + 1, s_sdiv, s_hdiv, s_luts);
+            o.z = pointwise_px(P, v.z, x + 2, s_sdiv, s_hdiv, s_luts);
+            o.w = pointwise_px(P, v.w, x + 3, s_sdiv, s_hdiv, s_luts);
+            *reinterpret_cast<uint4*>(dp) = o;
         } else {
-            const bool tail = x >= P.w - (P.w & 31);
-            o = hsv_to_rgb(P.hlut[hh], P.slut[ss], P.vlut[vv], tail) | (p & 0xFF000000u);
+            for (int k = 0; k < VEC && x + k < P.w; ++k)
+                reinterpret_cast<uint32_t*>(dp)[k] =
+                    pointwise_px(P, reinterpret_cast<const uint32_t*>(sp)[k], x + k, s_sdiv, s_hdiv, s_luts);
         }
     }
-    reinterpret_cast<uint32_t*>(P.dst + (int64_t)y * P.dstride)[x] = o;
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -281,7 +472,7 @@ static int upload_hsv_tables()
     if (dev == uploaded_dev) return MVB_OK;
     HsvTables t;
     host_hsv_tables(t);
-    cudaError_t e = cudaMemcpyToSymbol(c_hsv, &t, sizeof t);
+    cudaError_t e = cudaMemcpyToSymbol(g_hsv, &t, sizeof t);
     if (e != cudaSuccess) return set_error(MVB_ERR_CUDA, cudaGetErrorString(e));
     uploaded_dev = dev;
     return MVB_OK;
@@ -375,8 +566,16 @@ extern "C" int mvb_effect_blur_rgba8(const void* src, int32_t w, int32_t h, int6
     std::memcpy(P.wt, weights, sizeof(uint16_t) * (size_t)k);
     const int W2 = w + 2 * k, H2 = h + 2 * k;
     cudaStream_t st = (cudaStream_t)stream;
-    k_blur_h_rgba<<<dim3((W2 + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
-    k_blur_v_rgba<<<dim3((W2 + 31) / 32, (H2 + 7) / 8), 256, 0, st>>>(P);
+    bool tiled = k <= kTiledMaxK;
+    for (int j = 0; j < k; j++) tiled = tiled && weights[j] <= 255;   // IDP.2A takes 8-bit weights
+    if (tiled) {
+        const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);
+        k_blur_h_rgba_tiled<<<dim3((W2 + kBlurHOut - 1) / kBlurHOut, h), 256, (n_in + k + 12) * 4, st>>>(P);
+        k_blur_v_rgba_tiled<<<dim3((W2 + 31) / 32, (H2 + 31) / 32), 256, 0, st>>>(P);
+    } else {
+        k_blur_h_rgba<<<dim3((W2 + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
+        k_blur_v_rgba<<<dim3((W2 + 31) / 32, (H2 + 7) / 8), 256, 0, st>>>(P);
+    }
     return check_launch("mvb_effect_blur_rgba8");
 }
 
@@ -408,8 +607,14 @@ extern "C" int mvb_effect_drop_shadow_rgba8(const void* src, int32_t w, int32_t 
         P.mode = MVB_BLUR_PLAIN;
         std::memset(P.lut, 0, 256);
         std::memcpy(P.wt, weights, sizeof(uint16_t) * (size_t)k);
-        k_blur_h_alpha<<<dim3((Ws + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
-        k_blur_v_alpha<<<dim3((Ws + 31) / 32, (Hs + 7) / 8), 256, 0, st>>>(P);
+        if (k <= kTiledMaxK) {
+            const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);
+            k_blur_h_alpha_tiled<<<dim3((Ws + kBlurHOut - 1) / kBlurHOut, h), 256, (n_in + k + 12) * 4, st>>>(P);
+            k_blur_v_alpha_tiled<<<dim3((Ws + 31) / 32, (Hs + 31) / 32), 256, 0, st>>>(P);
+        } else {
+            k_blur_h_alpha<<<dim3((Ws + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
+            k_blur_v_alpha<<<dim3((Ws + 31) / 32, (Hs + 7) / 8), 256, 0, st>>>(P);
+        }
         S.a1 = plane;
     }
     S.src = static_cast<const uint8_t*>(src);
@@ -435,7 +640,12 @@ static int launch_pointwise(PointParams& P, const void* src, int w, int h, int64
     P.src = static_cast<const uint8_t*>(src);
     P.dst = static_cast<uint8_t*>(dst);
     P.w = w; P.h = h; P.sstride = (int32_t)sstride; P.dstride = (int32_t)dstride;
-    k_pointwise<<<dim3((w + 31) / 32, (h + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P);
+    const bool vec = !((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
+                        (uintptr_t)sstride | (uintptr_t)dstride) & 15);
+    const long long work = (long long)((w + (vec ? 3 : 0)) / (vec ? 4 : 1)) * h;
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 148 * 8);
+    if (vec) k_pointwise<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+    else k_pointwise<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
     return check_launch(what);
 }
 
