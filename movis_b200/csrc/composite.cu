@@ -1,20 +1,13 @@
-// composite.cu -- fused multi-layer warp + blend kernel and the stand-alone warp / alpha_composite
-// operators (sm_100a).  C ABI in include/movis_b200.h.
+// composite.cu -- C-ABI entry points and host side of the fused multi-layer warp + blend kernel,
+// plus the stand-alone warp / alpha_composite operators (sm_100a).  C ABI in include/movis_b200.h.
 //
-// Replaces, per frame, the reference's per-layer pair cv2.warpAffine -> alpha_composite
-// (movis/layer/composition.py:811-819) and the frame walk around it (composition.py:363-368).
-//
-// Data layout: frame and sources are uint8 RGBA HWC in HBM.  One CTA owns a 32x32 output tile:
-//   prologue  - cull layers whose bbox misses the tile; for the survivors build, in shared memory,
-//               cv::warpAffine's integer tables restricted to the tile (adelta/bdelta for the 32
-//               columns, X0/Y0 for the 32 rows; fp64 without FMA contraction) and a 256-entry
-//               alpha LUT that applies the layer opacity exactly like the reference path does;
-//   main loop - each thread owns one column and 8 rows of the tile (pixels parked in shared memory,
-//               re-quantised to 4xu8 after every layer, as the reference does).  Layers are the
-//               OUTER loop: per layer the thread loads the descriptor once, samples its rows
-//               (4 bilinear taps gathered through L1, cv2's fixed-point weights) into shared
-//               memory, then jumps once to the blend loop specialised for the layer's mode;
-//   epilogue  - one coalesced 128-byte store per warp row.  The frame is written exactly once.
+// mvb_composite_stack replaces, per frame, the reference's per-layer pair cv2.warpAffine ->
+// alpha_composite (movis/layer/composition.py:811-819) and the frame walk around it
+// (composition.py:363-368).  The device code lives in stack_float.cuh (arithmetic, walk_layer, the
+// one-CTA-per-tile form) and stack_ws.cuh (the persistent warp-specialised kernel that is launched);
+// this file turns mvb_layer records into device records, picks the TMA box of every layer, keeps the
+// cache of TMA descriptors and launches.  Frame and sources are uint8 RGBA HWC in HBM; the frame is
+// written exactly once per launch.
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -33,11 +26,8 @@
 namespace mvb {
 
 constexpr int kTileW = 32;
-constexpr int kRows = 8;             // rows per thread
-constexpr int kWarps = 4;
-constexpr int kTileH = kRows * kWarps;
-constexpr int kMaxLayers = 32; // per launch; 32 * 104 B of descriptors stay under the 4 KB param limit
-constexpr int kSlots = 16;     // layers whose per-tile tables are resident in shared memory at a time
+constexpr int kTileH = 32;
+constexpr int kMaxLayers = 32; // per launch: device records + TMA descriptors travel as kernel parameters (8.6 KB)
 
 struct DevLayer {
     // --- first 64 bytes: what the per-tile cull / classification reads (copied to shared memory) ---
@@ -84,51 +74,6 @@ constexpr int kPilOver = 18; // dispatch code of PIL's "over" next to the 18 num
 struct BlendTableData { uint32_t rcp24[260]; uint32_t softg[256]; };
 __device__ BlendTableData g_blend_tables;
 
-// Phase 2 of one layer: blend the samples parked in shared memory into the thread's pixels.
-// MODE is a template parameter (18 numpy modes + PIL "over"), so the loop has no per-pixel
-// dispatch.  OPAQUE: the frame's alpha is 255 everywhere (opaque bg_color), which both "over"
-// operators preserve -- the division-free arithmetic is then the only code that exists.
-template <int MODE, bool OPAQUE>
-__device__ __forceinline__ void blend_rows(const uint32_t* __restrict__ smpcol, uint32_t* __restrict__ pxcol,
-                                           int r0, int r1, const BlendTables& tabs)
-{
-#pragma unroll 1
-    for (int row = r0; row < r1; ++row) {
-        const uint32_t sp = smpcol[row * kTileW]; // r, g, b, opacity-scaled alpha
-        const uint32_t px = pxcol[row * kTileW];
-        const uint32_t fa = sp >> 24;
-        uint32_t out;
-        if (fa == 0) {
-            // PIL: no-op.  numpy: no-op unless bg alpha is 0, where rgb is zeroed (imgproc.py:164)
-            if (OPAQUE || MODE == kPilOver || px >= 0x01000000u) continue;
-            out = 0;
-        } else if (OPAQUE || px >= 0xFF000000u) {
-            const uint32_t sr = sp & 0xFFu, sg = __byte_perm(sp, 0, 0x4441), sb = __byte_perm(sp, 0, 0x4442);
-            const uint32_t dr = px & 0xFFu, dg = __byte_perm(px, 0, 0x4441), db = __byte_perm(px, 0, 0x4442);
-            const uint32_t ia = 255 - fa;
-            uint32_t r, g, b;
-            if constexpr (MODE == kPilOver) {
-                const uint32_t tr = 128 * (sr * fa + dr * ia) + 0x4000;
-                const uint32_t tg = 128 * (sg * fa + dg * ia) + 0x4000;
-                const uint32_t tb = 128 * (sb * fa + db * ia) + 0x4000;
-                r = (((tr >> 8) + tr) >> 8) >> 7;
-                g = (((tg >> 8) + tg) >> 8) >> 7;
-                b = (((tb >> 8) + tb) >> 8) >> 7;
-            } else {
-                r = div255(fa * blend_target_tab<MODE>(dr, sr, tabs) + ia * dr);
-                g = div255(fa * blend_target_tab<MODE>(dg, sg, tabs) + ia * dg);
-                b = div255(fa * blend_target_tab<MODE>(db, sb, tabs) + ia * db);
-            }
-            out = r | (g << 8) | (b << 16) | 0xFF000000u;
-        } else if constexpr (MODE == kPilOver) {
-            out = over_pil(px, unpack(sp), fa);
-        } else {
-            out = over_numpy<MODE>(px, unpack(sp), fa, false);
-        }
-        pxcol[row * kTileW] = out;
-    }
-}
-
 enum { kTileEdge = 0, kTileEmpty = 1, kTileInterior = 2 };
 
 } // namespace mvb
@@ -137,198 +82,6 @@ enum { kTileEdge = 0, kTileEmpty = 1, kTileInterior = 2 };
 #include "stack_ws.cuh"      // k_stack_ws: its persistent, warp-specialised form (default)
 
 namespace mvb {
-
-// One CTA per kTileW x kTileH output tile (thread = 1 column x kRows rows).
-template <bool OPAQUE>
-__global__ void __launch_bounds__(kWarps * 32)
-k_composite_stack(const __grid_constant__ StackParams P)
-{
-    __shared__ int2 s_col[kSlots][kTileW];         // (adelta, bdelta) per tile column
-    __shared__ int2 s_row[kSlots][kTileH];         // (X0, Y0) per tile row
-    __shared__ uint8_t s_lut[kSlots][256];         // opacity-scaled alpha
-    __shared__ uint32_t s_px[kTileH][kTileW];      // the tile's pixels while the stack is walked
-    __shared__ uint32_t s_smp[kTileH][kTileW];     // the current layer's samples
-    __shared__ uint32_t s_rcp24[260];
-    __shared__ uint32_t s_softg[256];
-    __shared__ int s_active[kMaxLayers];
-    __shared__ int s_class[kMaxLayers];
-    __shared__ int s_nactive;
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
-
-    // ---- cull + classify the layers against this tile -------------------------------------------
-    if (warp == 0) {
-        bool hit = false;
-        int cls = kTileEdge;
-        if (lane < P.n_layers) {
-            const DevLayer& L = P.layers[lane];
-            // tile ∩ bbox ∩ frame, in bbox coordinates (inclusive corners)
-            const int u0 = max(tx0, L.bx) - L.bx, u1 = min(min(tx0 + kTileW, L.bx + L.bw), P.W) - 1 - L.bx;
-            const int v0 = max(ty0, L.by) - L.by, v1 = min(min(ty0 + kTileH, L.by + L.bh), P.H) - 1 - L.by;
-            hit = L.bw > 0 && L.bh > 0 && u0 <= u1 && v0 <= v1;
-            if (hit) {
-                // source-space extent of that rectangle (affine: extrema at the corners); 0.25 px of
-                // slack covers the 1/32 px coordinate quantisation and its +16/1024 rounding offset
-                double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const double u = (k & 1) ? u1 : u0, v = (k & 2) ? v1 : v0;
-                    const double xs = L.m[0] * u + L.m[1] * v + L.m[2];
-                    const double ys = L.m[3] * u + L.m[4] * v + L.m[5];
-                    xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
-                    ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
-                }
-                const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == kTileH - 1;
-                if (xmax < -1.25 || xmin > L.src_w + 0.25 || ymax < -1.25 || ymin > L.src_h + 0.25)
-                    cls = kTileEmpty;      // no tap of this tile falls inside the source
-                else if (full && xmin > 0.25 && xmax < L.src_w - 1.25 && ymin > 0.25 && ymax < L.src_h - 1.25)
-                    cls = kTileInterior;   // whole tile covered and every tap inside the source
-                // an empty tile is a no-op for PIL, and for numpy too when the frame is opaque
-                if (cls == kTileEmpty && (L.pil || OPAQUE)) hit = false;
-            }
-        }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) {
-            const int slot = __popc(m & ((1u << lane) - 1u));
-            s_active[slot] = lane;
-            s_class[slot] = cls;
-        }
-        if (lane == 0) s_nactive = __popc(m);
-    }
-    if (P.needs_tables) {
-        for (int i = tid; i < 260; i += kWarps * 32) s_rcp24[i] = g_blend_tables.rcp24[i];
-        for (int i = tid; i < 256; i += kWarps * 32) s_softg[i] = g_blend_tables.softg[i];
-    }
-    const BlendTables tabs{s_rcp24, s_softg};
-
-    // ---- the thread's pixels: column `lane`, rows [kRows warp, kRows warp + kRows) ---------------
-    const int x = tx0 + lane;
-    const int rbeg = warp * kRows;
-    const int rend = min(rbeg + kRows, P.H - ty0);
-    const bool x_ok = x < P.W;
-    uint32_t* const pxcol = &s_px[0][lane];
-    uint32_t* const smpcol = &s_smp[0][lane];
-    if (x_ok) {
-        for (int row = rbeg; row < rend; ++row) {
-            uint32_t v = P.bg;
-            if (P.keep_frame) v = reinterpret_cast<const uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x];
-            pxcol[row * kTileW] = v;
-        }
-    }
-    __syncthreads();
-    const int n_active = s_nactive;
-
-    // ---- walk the stack in paint order, kSlots layers' tables at a time --------------------------
-    for (int base = 0; base < n_active; base += kSlots) {
-        const int n_here = min(kSlots, n_active - base);
-        if (base > 0) __syncthreads();
-        for (int i = tid; i < n_here * (kTileW + kTileH); i += kWarps * 32) {
-            const int slot = i / (kTileW + kTileH), j = i % (kTileW + kTileH);
-            if (s_class[base + slot] == kTileEmpty) continue;
-            const DevLayer& L = P.layers[s_active[base + slot]];
-            if (j < kTileW) {
-                const int u = tx0 + j - L.bx;
-                s_col[slot][j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
-            } else {
-                const int v = ty0 + (j - kTileW) - L.by;
-                s_row[slot][j - kTileW] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
-            }
-        }
-        for (int i = tid; i < n_here * 256; i += kWarps * 32) {
-            const int slot = i >> 8, a = i & 255;
-            if (s_class[base + slot] == kTileEmpty) continue;
-            const DevLayer& L = P.layers[s_active[base + slot]];
-            uint32_t v = (uint32_t)a;
-            if (L.opacity < 1.0)
-                v = L.pil ? (uint32_t)(a * L.pil_a) / 255u                      // imgproc.py:206-208
-                          : __double2uint_rz(__dmul_rn((double)a, L.opacity));  // imgproc.py:159
-            s_lut[slot][a] = (uint8_t)v;
-        }
-        __syncthreads();
-        if (!x_ok) continue;
-
-#pragma unroll 1
-        for (int slot = 0; slot < n_here; ++slot) {
-            const DevLayer& L = P.layers[s_active[base + slot]];
-            const int cls = s_class[base + slot];
-            int r0 = rbeg, r1 = rend;
-            if (cls != kTileInterior) {
-                if ((unsigned)(x - L.bx) >= (unsigned)L.bw) continue;
-                r0 = max(rbeg, L.by - ty0);
-                r1 = min(rend, L.by + L.bh - ty0);
-                if (r0 >= r1) continue;
-            }
-            if (cls == kTileEmpty) { // numpy path on a non-opaque frame, every sample transparent
-                for (int row = r0; row < r1; ++row)
-                    if (pxcol[row * kTileW] < 0x01000000u) pxcol[row * kTileW] = 0;
-                continue;
-            }
-            // phase 1: sample the layer at the thread's pixels (mode-independent code)
-            {
-                const uint8_t* __restrict__ src = L.src;
-                const int ss = L.src_stride;
-                const int2 col = s_col[slot][lane];
-                const int2* __restrict__ rowtab = s_row[slot];
-                const uint8_t* __restrict__ lut = s_lut[slot];
-                if (cls == kTileInterior) {
-                    // all kRows rows, every tap inside the source: 4 rows at a time, their 16 taps
-                    // requested before the first one is used
-#pragma unroll 1
-                    for (int g = 0; g < kRows; g += 4) {
-                        uint32_t t[4][4], fx[4], fy[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int2 r = rowtab[rbeg + g + k];
-                            const int X = (r.x + col.x) >> 5, Y = (r.y + col.y) >> 5;
-                            const uint8_t* base = src + ((uint32_t)(Y >> 5) * (uint32_t)ss + (uint32_t)(X >> 5) * 4u);
-                            t[k][0] = ldg_u32(base);
-                            t[k][1] = ldg_u32(base + 4);
-                            t[k][2] = ldg_u32(base + ss);
-                            t[k][3] = ldg_u32(base + ss + 4);
-                            fx[k] = X & 31;
-                            fy[k] = Y & 31;
-                        }
-                        Rgba q[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) q[k] = bilinear_q5(t[k][0], t[k][1], t[k][2], t[k][3], fx[k], fy[k]);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) q[k].a = lut[q[k].a];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            smpcol[(rbeg + g + k) * kTileW] = q[k].r | (q[k].g << 8) | (q[k].b << 16) | (q[k].a << 24);
-                    }
-                } else {
-                    const int sw = L.src_w, sh = L.src_h;
-#pragma unroll 1
-                    for (int row = r0; row < r1; ++row) {
-                        const int2 r = rowtab[row];
-                        Rgba s;
-                        uint32_t sp = 0;
-                        if (sample_q5(src, sw, sh, ss, (r.x + col.x) >> 5, (r.y + col.y) >> 5, s))
-                            sp = s.r | (s.g << 8) | (s.b << 16) | ((uint32_t)lut[s.a] << 24);
-                        smpcol[row * kTileW] = sp;
-                    }
-                }
-            }
-            // phase 2: blend, in the loop specialised for this layer's mode
-            switch (L.pil ? kPilOver : L.mode) {
-#define MVB_ROWS(M) case M: blend_rows<M, OPAQUE>(smpcol, pxcol, r0, r1, tabs); break;
-                MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
-                MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
-                MVB_ROWS(15) MVB_ROWS(16) MVB_ROWS(17) MVB_ROWS(18)
-#undef MVB_ROWS
-            default: break;
-            }
-        }
-    }
-
-    // ---- epilogue: one coalesced 128-byte store per warp row ---------------------------------------
-    if (x_ok)
-        for (int row = rbeg; row < rend; ++row)
-            reinterpret_cast<uint32_t*>(P.frame + (int64_t)(ty0 + row) * P.stride)[x] = pxcol[row * kTileW];
-}
 
 // cv2.warpAffine stand-alone: one thread per destination pixel.
 __global__ void __launch_bounds__(256)
@@ -586,7 +339,11 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
             const int m = P.layers[i].mode;
             if (!P.layers[i].pil && (m == 6 || m == 7 || m == 11 || m == 12)) P.needs_tables = 1;
         }
-        if (opaque) {
+        static const std::string which = [] {   // diagnostics: MVB_STACK_KERNEL=tile selects the one-CTA-per-tile form
+            const char* e = std::getenv("MVB_STACK_KERNEL");
+            return std::string(e ? e : "");
+        }();
+        {
             int stage = 0;
             for (int i = 0; i < n; i++) {
                 DevLayer& L = P.layers[i];
@@ -599,26 +356,24 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
             cudaGetDevice(&dev);
             if (dev != smem_dev) {
                 cudaFuncSetAttribute(k_stack_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxStageBytes);
-                cudaFuncSetAttribute(k_stack_ws, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                cudaFuncSetAttribute(k_stack_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     4 * kMaxStageBytes + kMaxLayers * 1024);
+                cudaFuncSetAttribute(k_stack_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      4 * kMaxStageBytes + kMaxLayers * 1024);
                 cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
                 smem_dev = dev;
             }
             PT.stage_bytes = (stage + 127) & ~127;
             PT.stages_log2 = 4 * PT.stage_bytes <= 36 * 1024 ? 2 : 1;   // keep 3-4 CTAs per SM resident
-            static const bool tile_kernel = [] {   // diagnostics: MVB_STACK_KERNEL=tile selects the one-CTA-per-tile form
-                const char* e = std::getenv("MVB_STACK_KERNEL");
-                return e && std::string(e) == "tile";
-            }();
-            if (tile_kernel) {
+            if (which == "tile" && opaque) {
                 k_stack_opaque<<<grid, kFWarps * 32, PT.stage_bytes << PT.stages_log2, stream>>>(PT);
             } else {
                 const int n_tiles = (int)(grid.x * grid.y);
                 const int ctas = n_tiles < 3 * n_sm ? n_tiles : 3 * n_sm;
-                k_stack_ws<<<ctas, kWsThreads, (PT.stage_bytes << PT.stages_log2) + n * 1024, stream>>>(PT);
+                const size_t smem = ((size_t)PT.stage_bytes << PT.stages_log2) + (size_t)n * 1024;
+                if (opaque) k_stack_ws<true><<<ctas, kWsThreads, smem, stream>>>(PT);
+                else k_stack_ws<false><<<ctas, kWsThreads, smem, stream>>>(PT);
             }
-        } else {
-            k_composite_stack<false><<<grid, kWarps * 32, 0, stream>>>(P);
         }
         done += n;
         first = false;

@@ -138,8 +138,9 @@ __device__ __forceinline__ u64 ratio255_biased(u64 n, u64 den)
     return min2(add2_rm(t, bc(kMagic)), bc(kMagic + 255.0f));
 }
 
+// T(b, f) - b for one colour channel of two rows, biased inputs.
 template <int MODE>
-__device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const uint32_t* softg)
+__device__ __forceinline__ u64 blend_diff2(u64 dB, u64 sB, const uint32_t* softg)
 {
     const u64 kM = bc(kMagic), kM255 = bc(kMagic + 255.0f);
     u64 diff;
@@ -195,8 +196,16 @@ __device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const uint32_t
         static_assert(MODE == 17, "unknown blend mode");
         diff = max2(sub2(kM, dB), sub2(kM, sB));
     }
-    // x = fa*T + (255 - fa)*b = fa*(T - b) + 255*b, an integer in [0, 65025]
-    const u64 x = fma2(fa, diff, fma2(dB, bc(255.0f), bc(kNeg255Magic)));
+    return diff;
+}
+
+// Opaque frame (alpha 255 before and after): blend + composite + requantise one colour channel of
+// two rows.  x = fa*T + (255 - fa)*b = fa*(T - b) + 255*b is an integer in [0, 65025].
+template <int MODE>
+__device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const uint32_t* softg)
+{
+    const u64 kM = bc(kMagic);
+    const u64 x = fma2(fa, blend_diff2<MODE>(dB, sB, softg), fma2(dB, bc(255.0f), bc(kNeg255Magic)));
     if constexpr (MODE == 18) return fma2(x, bc(kInv255), kM);                    // PIL: floor((x+127)/255) = rint(x/255)
     else return fma2_rm(x, bc(kInv255), kM);                                      // numpy: floor(x/255)
 }
@@ -206,7 +215,7 @@ constexpr int kFRows = 4;
 constexpr int kFTileH = kFWarps * kFRows;
 constexpr int kFSlots = 8;   // layers whose per-tile tables are resident in shared memory at a time
 
-struct RowPairState { u64 c[3]; };   // r, g, b of rows (2p, 2p+1), biased
+struct RowPairState { u64 c[4]; };   // r, g, b, a of rows (2p, 2p+1), biased (a is unused on opaque frames)
 
 // Everything the layer loop reads about one resident layer, contiguous so that one base address
 // serves all of it (offsets become LDS immediates).
@@ -218,14 +227,87 @@ struct __align__(16) SlotMem {
     float lut[256];          // opacity-scaled alpha, as float
 };
 
+// ---- frames whose alpha is not known to be 255 ("general") ----------------------------------------
+// numpy _overlay (imgproc.py:156-170), matte NONE, two rows: with c1 = 255 fa, c2 = ba (255 - fa),
+// oa = c1 + c2:  rgb = (c1 T + c2 b) // max(oa, 1),  alpha = oa // 255.  The numerator
+// c1 (T - b) + oa b is below 2^24, so it is exact in fp32; the quotient by the variable oa is
+// q0 = rint(n * rcp(oa)) corrected by the sign of the exact remainder n - q0 oa (|n/oa - q0| < 1).
 template <int MODE>
+__device__ __forceinline__ void over_numpy_rows(RowPairState& d, const u64 (&s)[4], u64 fa, const uint32_t* softg)
+{
+    const u64 kM = bc(kMagic);
+    const u64 ba = sub2(d.c[3], kM);
+    const u64 c1 = mul2(fa, bc(255.0f));
+    const u64 oa = fma2(ba, sub2(bc(255.0f), fa), c1);
+    const u64 oam = max2(oa, bc(1.0f));                       // oa == 0: numerator 0, quotient 0 (imgproc.py:164)
+    const u64 rd = rcp2(oam);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const u64 diff = blend_diff2<MODE>(d.c[c], s[c], softg);
+        const u64 n = fma2(c1, diff, mul2(oa, sub2(d.c[c], kM)));
+        const u64 t = fma2(n, rd, kM);                        // magic + rint(n / oa)
+        float r0, r1, t0, t1;
+        upk(fma2(sub2(kM, t), oam, n), r0, r1);               // n - q0 oa, exact, in (-oa, oa)
+        upk(t, t0, t1);
+        d.c[c] = pk(__uint_as_float(__float_as_uint(t0) + (uint32_t)(__float_as_int(r0) >> 31)),   // q0 - (r < 0)
+                    __uint_as_float(__float_as_uint(t1) + (uint32_t)(__float_as_int(r1) >> 31)));
+    }
+    d.c[3] = fma2_rm(oa, bc(kInv255), kM);
+}
+
+// PIL ImagingAlphaComposite (reached from imgproc.py:210-213), two rows:
+//   outa255 = 255 sa + da (255 - sa);  coef1 = sa*255*255*128 // outa255;  coef2 = 255*128 - coef1
+//   t = s coef1 + d coef2 + 0x4000;  out = (((t >> 8) + t) >> 8) >> 7 = (t + (t >> 8)) >> 15
+//   alpha: u = outa255 + 0x80;  out = ((u >> 8) + u) >> 8
+// sa == 0 gives coef1 = 0 and reproduces d exactly, which is PIL's "leave the pixel alone" rule.
+// coef1 needs a 31-bit numerator: integer division, once per pixel.
+__device__ __forceinline__ void over_pil_rows(RowPairState& d, const u64 (&s)[4], u64 fa)
+{
+    const u64 kM = bc(kMagic);
+    float f0, f1, a0, a1;
+    upk(fa, f0, f1);
+    upk(d.c[3], a0, a1);
+    const uint32_t sa0 = __float_as_uint(f0 + kMagic) & 0xFFu, sa1 = __float_as_uint(f1 + kMagic) & 0xFFu;
+    const uint32_t da0 = __float_as_uint(a0) & 0xFFu, da1 = __float_as_uint(a1) & 0xFFu;
+    const uint32_t oa0 = sa0 * 255u + da0 * (255u - sa0), oa1 = sa1 * 255u + da1 * (255u - sa1);
+    const uint32_t k0 = (sa0 * 8323200u) / max(oa0, 1u), k1 = (sa1 * 8323200u) / max(oa1, 1u);
+    const u64 c1 = pk((float)k0, (float)k1), c2 = sub2(bc(32640.0f), c1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const u64 t = fma2(sub2(s[c], kM), c1, fma2(sub2(d.c[c], kM), c2, bc(16384.0f)));   // < 2^24
+        const u64 v = add2(t, sub2(fma2_rm(t, bc(1.0f / 256.0f), kM), kM));                 // t + (t >> 8)
+        d.c[c] = fma2_rm(v, bc(1.0f / 32768.0f), kM);
+    }
+    const u64 u = pk((float)(oa0 + 128u), (float)(oa1 + 128u));
+    const u64 v = add2(u, sub2(fma2_rm(u, bc(1.0f / 256.0f), kM), kM));
+    d.c[3] = fma2_rm(v, bc(1.0f / 256.0f), kM);
+}
+
+// Blend the samples of four rows into the thread's pixels.  `keep`: bit q set = row q of this thread
+// lies inside the layer's bbox (only consulted on general frames, where a transparent sample is
+// not a no-op for the numpy arithmetic).
+template <int MODE, bool OPAQUE>
 __device__ __forceinline__ void blend_rows(RowPairState (&d)[2], const u64 (&s)[2][4], const u64 (&fa)[2],
-                                           const uint32_t* softg)
+                                           const uint32_t* softg, unsigned keep)
 {
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < 2; ++p) {
+        if constexpr (OPAQUE) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) d[p].c[c] = blend_chan<MODE>(d[p].c[c], s[p][c], fa[p], softg);
+            for (int c = 0; c < 3; ++c) d[p].c[c] = blend_chan<MODE>(d[p].c[c], s[p][c], fa[p], softg);
+        } else {
+            RowPairState nd = d[p];
+            if constexpr (MODE == 18) over_pil_rows(nd, s[p], fa[p]);
+            else over_numpy_rows<MODE>(nd, s[p], fa[p], softg);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float o0, o1, n0, n1;
+                upk(d[p].c[c], o0, o1);
+                upk(nd.c[c], n0, n1);
+                d[p].c[c] = pk((keep >> (2 * p) & 1) ? n0 : o0, (keep >> (2 * p + 1) & 1) ? n1 : o1);
+            }
+        }
+    }
 }
 
 // ---- TMA / mbarrier plumbing (PTX; sm_90+ async proxy) -------------------------------------------
@@ -289,7 +371,7 @@ struct PixelCtx {
 // One layer of the walk for one thread: fetch the taps of its four rows (from the TMA-staged box,
 // or through L1 for layers that cannot be staged), cv2's fixed-point bilinear, opacity LUT, blend
 // into the pixels `d`.  `before_tma_wait(info)` runs ahead of the wait on the stage's barrier.
-template <class Slot, class BeforeTmaWait>
+template <bool OPAQUE, class Slot, class BeforeTmaWait>
 __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, int layer_index, const PixelCtx& C,
                                            RowPairState (&d)[2], const uint32_t* softg, BeforeTmaWait&& before_tma_wait)
 {
@@ -367,6 +449,8 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
             if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) {
                 const Taps tp = fetch_taps(src, sw, sh, ss, sumx >> 5, sumy >> 5);
                 t[k][0] = tp.p00; t[k][1] = tp.p01; t[k][2] = tp.p10; t[k][3] = tp.p11;
+            } else {
+                ok &= ~(1u << k);
             }
             fxs[k] = (float)(sumx & 0x3E0);
             wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
@@ -416,7 +500,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
 
     // ---- blend, in the code specialised for this layer's mode ------------------------------------
     switch (info.x & 255) {
-#define MVB_ROWS(M) case M: blend_rows<M>(d, s, fa, softg); break;
+#define MVB_ROWS(M) case M: blend_rows<M, OPAQUE>(d, s, fa, softg, ok); break;
         MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
         MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
         MVB_ROWS(15) MVB_ROWS(16) MVB_ROWS(17) MVB_ROWS(18)
@@ -598,7 +682,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
 
 #pragma unroll 1
         for (int slot = 0; slot < n_here; ++slot) {
-            walk_layer(P, s_slot[slot], s_layer[slot] & 255, px, d, s_softg, [&](const int4& info) {
+            walk_layer<true>(P, s_slot[slot], s_layer[slot] & 255, px, d, s_softg, [&](const int4& info) {
                 if (tid == 0 && (info.x & (1 << 12))) {   // the stage of layer k-1 is free once every warp has read it
                     const int k = s_layer[slot] >> 8;
                     mbar_wait(bar_empty + 8 * ((k - 1) & ns_mask), ((k - 1) >> ns_log2) & 1);

@@ -42,6 +42,9 @@ struct __align__(16) UnitMem {
     UnitSlot slot[kWsSlots];
 };
 
+// OPAQUE: the frame's alpha is 255 throughout (opaque bg_color); otherwise alpha is carried as a
+// fourth channel and both "over" operators use their general forms (over_numpy_rows / over_pil_rows).
+template <bool OPAQUE>
 __global__ void __launch_bounds__(kWsThreads, 3)
 k_stack_ws(const __grid_constant__ StackParamsTma PT)
 {
@@ -150,7 +153,10 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                     const float yc = m3 * uc + m4 * vc + m5, ey = fabsf(m3) * hu + fabsf(m4) * hv;
                     const float xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
                     const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == kFTileH - 1;
-                    if (!(xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f)) {
+                    // No tap inside the source: every sample is transparent.  A no-op for PIL's over and on an
+                    // opaque frame; numpy's over still zeroes rgb where the frame's alpha is 0 (imgproc.py:164).
+                    const bool nothing = xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f;
+                    if (!(nothing && (OPAQUE || C[15] != 0))) {
                         cls = kTileEdge;
                         const int fx0 = ((int)floorf(xmin) - 1) & ~3, fy0 = (int)floorf(ymin) - 1;
                         if (box_w > 0 && (int)floorf(xmax) + 3 - fx0 <= box_w && (int)floorf(ymax) + 3 - fy0 <= box_h) {
@@ -248,17 +254,17 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
 #pragma unroll
                     for (int p = 0; p < 2; ++p)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
+                        for (int c = 0; c < 4; ++c)
                             d[p].c[c] = pk(__uint_as_float(__byte_perm(v[2 * p], kMagicBits, 0x7650 + c)),
                                            __uint_as_float(__byte_perm(v[2 * p + 1], kMagicBits, 0x7650 + c)));
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) d[0].c[c] = d[1].c[c] = bc(kMagic + (float)((P.bg >> (8 * c)) & 0xFFu));
+                    for (int c = 0; c < 4; ++c) d[0].c[c] = d[1].c[c] = bc(kMagic + (float)((P.bg >> (8 * c)) & 0xFFu));
                 }
             }
 #pragma unroll 1
             for (int slot = 0; slot < n_here; ++slot)
-                walk_layer(P, U.slot[slot], U.layer[slot], px, d, s_softg, [](const int4&) {});
+                walk_layer<OPAQUE>(P, U.slot[slot], U.layer[slot], px, d, s_softg, [](const int4&) {});
             __syncwarp();
             if (lane == 0) mbar_arrive(unit_empty + 8 * (u & (kWsUnits - 1)));   // this warp no longer reads the unit
             if ((hdr.z & 512) && x_ok) {   // last unit of the tile: one coalesced 128-byte store per warp row
@@ -271,7 +277,14 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                     upk(d[k >> 1].c[2], b0, b1);
                     const uint32_t rb = __float_as_uint((k & 1) ? r1 : r0), gb = __float_as_uint((k & 1) ? g1 : g0);
                     const uint32_t bb = __float_as_uint((k & 1) ? b1 : b0);
-                    const uint32_t pxl = __byte_perm(__byte_perm(rb, gb, 0x0040), bb, 0x0410) | 0xFF000000u;
+                    uint32_t pxl = __byte_perm(__byte_perm(rb, gb, 0x0040), bb, 0x0410);
+                    if constexpr (OPAQUE) {
+                        pxl |= 0xFF000000u;
+                    } else {
+                        float al0, al1;
+                        upk(d[k >> 1].c[3], al0, al1);
+                        pxl = __byte_perm(pxl, __float_as_uint((k & 1) ? al1 : al0), 0x4210);
+                    }
                     reinterpret_cast<uint32_t*>(P.frame + (int64_t)(ty0 + rbeg + k) * P.stride)[x] = pxl;
                 }
             }

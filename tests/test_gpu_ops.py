@@ -77,8 +77,9 @@ def test_every_mode_every_channel_pair_vs_oracle(dev):
                 assert np.array_equal(got, want), (ba, mode, matte)
 
 
-def _stack(dev, W, H, bg_color, layers, flags=0):
-    """mvb_composite_stack with identity-warp layers: (image, (x, y), mode, pil, opacity) in paint order."""
+def _stack(dev, W, H, bg_color, layers, flags=0, initial=None):
+    """mvb_composite_stack with identity-warp layers: (image, (x, y), mode, pil, opacity) in paint order.
+    ``initial`` + flags=1 (MVB_STACK_KEEP_FRAME) starts from given frame contents."""
     import torch
     rows = np.zeros(len(layers), dtype=dev.native.LAYER_DTYPE)
     keep = []
@@ -90,7 +91,7 @@ def _stack(dev, W, H, bg_color, layers, flags=0):
         rows[i]["M"] = [1, 0, 0, 0, 1, 0]
         rows[i]["bbox_x"], rows[i]["bbox_y"], rows[i]["bbox_w"], rows[i]["bbox_h"] = pos[0], pos[1], w, h
         rows[i]["blend_mode"], rows[i]["flags"], rows[i]["opacity"] = mode, 1 if pil else 0, op
-    frame = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    frame = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda") if initial is None else dev.up(initial)
     bg = np.asarray(bg_color, dtype=np.uint8)
     dev.native.check(dev.lib.mvb_composite_stack(frame.data_ptr(), W, H, frame.stride(0), bg.ctypes.data,
                                                  len(layers), rows.ctypes.data, flags, dev.stream()))
@@ -121,6 +122,30 @@ def test_opaque_stack_every_mode_every_value_triple_vs_oracle(dev):
             want = O.alpha_composite(A.copy(), B, (0, 0), op, mode % 18, 0, use_pil=pil)
             bad = np.nonzero((got != want).any(-1))
             assert len(bad[0]) == 0, (mode, op, len(bad[0]), got[bad][:3], want[bad][:3], A[bad][:3], B[bad][:3])
+
+
+def test_translucent_stack_every_alpha_pair_every_mode_vs_oracle(dev):
+    """The fused kernel's general instantiation (frame alpha carried as a fourth channel): every
+    (frame alpha, layer alpha) pair with random colours, 18 numpy modes + PIL's over, opacity 1 and
+    fractional, starting from given frame contents (MVB_STACK_KEEP_FRAME); the layer overhangs the
+    frame so that pixels outside its bbox must stay untouched."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    n = 1024                                   # 4 x 4 repeats of the 256 x 256 alpha-pair grid
+    yy, xx = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    F = rng.integers(0, 256, (n, n, 4), dtype=np.uint8)
+    F[..., 3] = yy & 255
+    F[:40, :40, :3] = [[0, 255, 128]]          # extremes
+    B = rng.integers(0, 256, (n - 64, n - 32, 4), dtype=np.uint8)
+    B[..., 3] = xx[: n - 64, : n - 32] & 255
+    pos = (-9, 40)
+    for mode in range(19):
+        pil = mode == 18
+        for op in (1.0, 0.37):
+            got = _stack(dev, n, n, (0, 0, 0, 0), [(B, pos, mode % 18, pil, op)], flags=1, initial=F)
+            want = O.alpha_composite(F.copy(), B, pos, op, mode % 18, 0, use_pil=pil)
+            bad = np.nonzero((got != want).any(-1))
+            assert len(bad[0]) == 0, (mode, op, len(bad[0]), got[bad][:3], want[bad][:3], F[bad][:3])
 
 
 def test_alpha_composite_fuzz_vs_oracle(dev):
