@@ -235,6 +235,10 @@ class LayerItem:
                 return None
             check_image_array(host, "Rendered layer image")
             frame = to_device(host)
+        return self.apply_effects_device(frame, layer_time)
+
+    def apply_effects_device(self, frame, layer_time: float):
+        """The effect chain of composition.py:829-830 on a CUDA image."""
         for effect in self._effects:
             if hasattr(effect, "apply_device"):
                 frame = effect.apply_device(frame, layer_time)

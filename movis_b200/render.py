@@ -93,11 +93,25 @@ def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
         ok = np.zeros(len(idx), dtype=bool)
         by_size: dict[tuple[int, int], list[int]] = {}
         images = [None] * len(idx)
-        for j, f in enumerate(idx):
-            image = item.fg_image_device(float(times[f]), comp.cache)
+        if isinstance(item.layer, Composition):
+            # Nested composition (composition.py: an inner Composition is just a layer, rendered with
+            # the default transparent background, its own cache and preview level): its frames for
+            # the whole range are planned and rendered as ONE batch, recursively, instead of one
+            # Python-level render per frame.
+            inner = item.layer
+            lt = layer_times[idx]
+            inside = np.nonzero((lt >= 0.0) & (lt < inner.duration))[0]
+            if len(inside):
+                batch = render_frames(inner, lt[inside], bg_color=(0, 0, 0, 0))
+                keep.append(batch)
+                for k, j in enumerate(inside):
+                    images[j] = item.apply_effects_device(batch[k], float(lt[j]))
+        else:
+            for j, f in enumerate(idx):
+                images[j] = item.fg_image_device(float(times[f]), comp.cache)
+        for j, image in enumerate(images):
             if image is None:
                 continue
-            images[j] = image
             by_size.setdefault((image.shape[1], image.shape[0]), []).append(j)
         for size, js in by_size.items():
             js_arr = np.asarray(js)
