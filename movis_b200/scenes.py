@@ -185,6 +185,43 @@ def build_s4(mv: Any, chroma_key_cls: Any, div: int = 1, duration: float = 5.0, 
 
 
 # ---------------------------------------------------------------------------------------------
+# S5 (config 4): 60 s 4K timeline, 24 layers + effects, the unit of the multi-GPU frame sharding
+# ---------------------------------------------------------------------------------------------
+
+def build_s5(mv: Any, chroma_key_cls: Any, div: int = 1, duration: float = 60.0, n_seq: int = 8):
+    """S2's 16 mixed-mode layers (keyframes stretched over the timeline) + S3's nested inner
+    composition (blur / drop shadow / glow inside) + S4's chroma-keyed frame sequence + 6 more
+    NORMAL 1080p layers: 24 layers, 1800 frames at 30 fps."""
+    W, H = 3840 // div, 2160 // div
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    sources = s2_sources(div)
+    for i in range(16):
+        item = comp.add_layer(
+            mv.layer.Image(sources[i]), name=f"l{i}",
+            position=((1400 + 70 * i) / div, (1040 + 5 * i) / div), blending_mode=BLEND_MODE_NAMES[i % 18])
+        _ramp(item.scale, 0.0, duration, (1.0, 1.0), (1.2, 1.2))
+        _ramp(item.rotation, 0.0, duration, float(2 * i - 15), float(15 - 2 * i))
+        _wrapped_ramp(item.opacity, duration, 0.2, 1.0, i / 16.0)
+    # nested inner composition of S3 (its own 1080p frame, transparent background)
+    inner = build_s3(mv, div=div, duration=duration)["nested"].layer
+    item = comp.add_layer(inner, name="nested", position=(W * 0.3, H * 0.35), opacity=0.9)
+    _ramp(item.scale, 0.0, duration, (0.8, 0.8), (1.1, 1.1))
+    _ramp(item.rotation, 0.0, duration, 0.0, 30.0)
+    # chroma-keyed sequence of S4, looping every n_seq frames
+    seq = mv.layer.ImageSequence.from_files(s4_sequence(div, n_seq), each_duration=duration / n_seq)
+    fg = comp.add_layer(seq, name="keyed", end_time=duration, opacity=0.8, scale=(0.6, 0.6),
+                        position=(W * 0.7, H * 0.68))
+    fg.add_effect(chroma_key_cls())
+    for i in range(6):
+        img = synthetic_rgba(5000 + i, 1080 // div, 1920 // div, alpha="random", rim=(32 // div) if i % 2 else 0)
+        item = comp.add_layer(mv.layer.Image(img), name=f"x{i}", opacity=0.35 + 0.1 * i,
+                              position=((900 + 400 * i) / div, (500 + 230 * i) / div))
+        _ramp(item.rotation, 0.0, duration, -20.0 + 8 * i, 25.0 - 6 * i)
+        _ramp(item.scale, 0.0, duration, (0.7, 0.7), (1.0, 1.0), "ease_in_out2")
+    return comp
+
+
+# ---------------------------------------------------------------------------------------------
 # generic mixed scene for parity fuzzing (overhanging layers, anisotropic scale, every mode)
 # ---------------------------------------------------------------------------------------------
 

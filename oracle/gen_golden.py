@@ -242,6 +242,7 @@ def main() -> None:
     shoot("s2v0t", scenes.build_s2(mv, div=12, variant=0), [1.0], (0, 0, 0, 0))  # transparent frame
     shoot("s3", scenes.build_s3(mv, div=6), [0.0, 2.5], (0, 0, 0, 255))
     shoot("s4", scenes.build_s4(mv, ChromaKey, div=12), [0.0, 1.01], (0, 0, 0, 255), levels=(1, 2, 4))
+    shoot("s5", scenes.build_s5(mv, ChromaKey, div=12, duration=6.0), [0.0, 3.1, 5.9], (0, 0, 0, 255), levels=(1, 2))
     # digests only (frames regenerated by the tests): denser time sampling of the headline scene
     shoot("s2v0d", scenes.build_s2(mv, div=12, variant=0), [round(0.1 + 0.4 * i, 3) for i in range(12)],
           (0, 0, 0, 255), store=False)

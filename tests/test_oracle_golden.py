@@ -150,7 +150,7 @@ def test_scene_walker_matches_reference_frames(golden):
                 if stored:
                     assert np.array_equal(got, g[key]), key
                 n += 1
-    assert n == 68
+    assert n == 74
 
 
 def test_reciprocal_table_division_is_exact():
