@@ -14,7 +14,13 @@ frame.  Metric: composited frames/sec (whole job, all GPUs).
             from pinned host memory and delivers every finished uint8 frame to pinned host memory
   roofline  achieved algorithmic GB/s of the fused kernel k_stack_ws (B_frame = 4*W*H + sum 4*w_l*h_l =
             165 888 000 B, each source texel and each output pixel counted once) / measured HBM peak;
-            `traffic` = dram bytes per launch from the committed ncu capture (profiles/roofline_traffic.json)
+            `traffic` = dram bytes per launch from the committed ncu capture (profiles/roofline_traffic.json).
+            One launch = one frame.  mvb_composite_frames alternates the frames of a batch between two
+            side streams (forked from / joined into the caller's stream) so that one frame's CTAs fill
+            the SMs the previous frame's last CTAs leave idle; `avg_launch_us` is therefore elapsed
+            time / launches over back-to-back batches (CUDA events on the caller's stream around the
+            fork and the join), and `serial_launch_us` is the same kernel launched one frame at a
+            time on the caller's stream (mvb_composite_stack), for comparison with ncu's durations
   cpu_baseline  the CPU oracle (a C + OpenMP port of the reference algorithm) on the host cores
 
 Multi-GPU: launched with torchrun, one rank per GPU; each rank renders its own contiguous 150-frame
@@ -234,12 +240,31 @@ def run_product(args) -> dict:
     k1.record()
     torch.cuda.synchronize()
     launch_s = k0.elapsed_time(k1) / 1e3 / (reps * FRAMES_PER_STEP)
+    # the same launches one at a time on the current stream (no overlap between frames)
+    from movis_b200 import _native
+    lib = _native.lib()
+    bg_arr = np.asarray(bg, dtype=np.uint8)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def serial():
+        for f in range(FRAMES_PER_STEP):
+            d = plan.descriptors[plan.offsets[f]:plan.offsets[f + 1]]
+            _native.check(lib.mvb_composite_stack(frames[f].data_ptr(), W, H, frames.stride(1), bg_arr.ctypes.data,
+                                                  len(d), d.ctypes.data, 0, stream))
+    serial()
+    torch.cuda.synchronize()
+    k0.record()
+    serial()
+    k1.record()
+    torch.cuda.synchronize()
+    serial_s = k0.elapsed_time(k1) / 1e3 / FRAMES_PER_STEP
     b_frame = scenes.s2_bytes_per_frame(1)
     peak, peak_src = measured_hbm_peak()
     achieved = b_frame / launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(), "kernel": "k_stack_ws",
-                "algorithmic_bytes_per_launch": b_frame, "avg_launch_us": launch_s * 1e6, "peak_source": peak_src}
+                "algorithmic_bytes_per_launch": b_frame, "avg_launch_us": launch_s * 1e6,
+                "serial_launch_us": serial_s * 1e6, "peak_source": peak_src}
 
     # --- e2e: host sources -> device, render, every frame back to pinned host memory ---------------
     h2d = sum(int(s.nbytes) for s in sources)

@@ -16,6 +16,8 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
 
@@ -385,6 +387,27 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
 
 using namespace mvb;
 
+// Two side streams (+ fork / join events) per device for mvb_composite_frames.
+constexpr int kLanes = 2;
+struct FrameLanes { cudaStream_t stream[kLanes]; cudaEvent_t fork, join[kLanes]; };
+
+static FrameLanes* frame_lanes()
+{
+    static thread_local std::vector<std::pair<int, FrameLanes>> per_device;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    for (auto& e : per_device)
+        if (e.first == dev) return &e.second;
+    FrameLanes L;
+    for (int k = 0; k < kLanes; k++) {
+        if (cudaStreamCreateWithFlags(&L.stream[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&L.join[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    per_device.emplace_back(dev, L);
+    return &per_device.back().second;
+}
+
 extern "C" int mvb_max_layers_per_launch(void) { return kMaxLayers; }
 
 extern "C" int mvb_composite_stack(void* frame, int32_t W, int32_t H, int64_t stride, const uint8_t bg_color[4],
@@ -404,15 +427,34 @@ extern "C" int mvb_composite_frames(int32_t n_frames, void* const* frames, int32
     if (int rc = require_device()) return rc;
     if (n_frames < 0 || (n_frames > 0 && (!frames || !layer_offsets)) || !bg_color)
         return set_error(MVB_ERR_INVALID_ARG, "bad frames / layer_offsets / bg_color");
-    for (int f = 0; f < n_frames; f++) {
-        if (int rc = check_image(frames[f], W, H, stride, "frame")) return rc;
-        const int n = layer_offsets[f + 1] - layer_offsets[f];
-        if (n < 0 || (n > 0 && !layers)) return set_error(MVB_ERR_INVALID_ARG, "layer_offsets must be non-decreasing");
-        if (int rc = launch_stack(frames[f], W, H, stride, bg_color, n, layers + layer_offsets[f], flags,
-                                  (cudaStream_t)stream))
-            return rc;
+    // Frames are independent, and the persistent kernel of one frame drains unevenly (the last CTAs
+    // of a launch leave SMs idle, and the next launch on the same stream waits for all of them): the
+    // frames of a run alternate between two side streams forked from `stream` and joined back into
+    // it, so the next frame's CTAs start on SMs as they come free.
+    FrameLanes* lanes = n_frames >= 2 ? frame_lanes() : nullptr;
+    cudaStream_t user = (cudaStream_t)stream;
+    if (lanes) {
+        cudaEventRecord(lanes->fork, user);
+        for (int k = 0; k < kLanes; k++) cudaStreamWaitEvent(lanes->stream[k], lanes->fork, 0);
     }
-    return MVB_OK;
+    int rc = MVB_OK;
+    for (int f = 0; f < n_frames && rc == MVB_OK; f++) {
+        rc = check_image(frames[f], W, H, stride, "frame");
+        if (rc) break;
+        const int n = layer_offsets[f + 1] - layer_offsets[f];
+        if (n < 0 || (n > 0 && !layers)) {
+            rc = set_error(MVB_ERR_INVALID_ARG, "layer_offsets must be non-decreasing");
+            break;
+        }
+        rc = launch_stack(frames[f], W, H, stride, bg_color, n, layers + layer_offsets[f], flags,
+                          lanes ? lanes->stream[f % kLanes] : user);
+    }
+    if (lanes)
+        for (int k = 0; k < kLanes; k++) {   // join, also after an error: `stream` must see whatever was enqueued
+            cudaEventRecord(lanes->join[k], lanes->stream[k]);
+            cudaStreamWaitEvent(user, lanes->join[k], 0);
+        }
+    return rc;
 }
 
 extern "C" int mvb_warp_affine_rgba8(const void* src, int32_t sw, int32_t sh, int64_t sstride, void* dst,
