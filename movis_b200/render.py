@@ -24,6 +24,9 @@ from .device import require_cuda, stream_ptr
 from .layer.composition import Composition, LayerItem, fill_descriptors, plan_affine
 
 
+PLAN_CHUNK = 64  # frames planned per host step of render_frames
+
+
 def shard_range(n_frames: int, rank: int, world_size: int) -> range:
     """Contiguous frame indices owned by ``rank``: [floor(r N / G), floor((r + 1) N / G))."""
     assert 0 <= rank < world_size
@@ -170,8 +173,12 @@ def render_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 
         assert out.stride(3) == 1 and out.stride(2) == 4
     if len(times) == 0:
         return out
-    plan = plan_range(comp, times)
-    launch_plan(plan, out, bg_color)
+    # Planned and enqueued in chunks: the device renders chunk i while the host evaluates the
+    # keyframes of chunk i + 1 (launches are asynchronous), so a batch costs max(host, device)
+    # instead of their sum.
+    for i in range(0, len(times), PLAN_CHUNK):
+        plan = plan_range(comp, times[i:i + PLAN_CHUNK])
+        launch_plan(plan, out[i:i + PLAN_CHUNK], bg_color)
     return out
 
 
