@@ -131,6 +131,8 @@ def dist_setup(n_gpus: int):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        from movis_b200.device import bind_host_to_gpu
+        bind_host_to_gpu(local)   # pinned frame buffers on the GPU's own NUMA node
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:

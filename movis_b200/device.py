@@ -25,6 +25,26 @@ def require_cuda() -> None:
         raise NoDeviceError("movis_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
 
 
+def bind_host_to_gpu(device_index: int) -> list[int]:
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA
+    node), so that pinned staging buffers allocated afterwards live next to that GPU's PCIe root.
+    Matters when several ranks deliver frames to host memory at once.  Returns the CPU list used
+    (empty when NVML or a usable CPU set is not available -- then nothing is changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        usable = sorted(ideal & os.sched_getaffinity(0))
+        if usable:
+            os.sched_setaffinity(0, usable)
+        return usable
+    except Exception:
+        return []
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
