@@ -117,6 +117,19 @@ def test_more_layers_than_one_launch():
     _assert_matches_oracle(comp, 1.1, (7, 7, 7, 255), level=2)
 
 
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (33, 31), (64, 32), (97, 65)])
+def test_tiny_and_ragged_frame_sizes_vs_oracle(size):
+    """Frames smaller than one 32 x 32 tile, exactly one tile, and ragged multiples, both background
+    alphas and draft levels, against the oracle."""
+    from movis_b200 import scenes
+    mv, _ = _mv()
+    comp = scenes.build_fuzz(mv, seed=21 + size[0], size=size, n_layers=10)
+    for bg in ((0, 0, 0, 0), (200, 100, 50, 255)):
+        _assert_matches_oracle(comp, 0.9, bg)
+    if min(size) >= 4:
+        _assert_matches_oracle(comp, 0.3, (1, 2, 3, 255), level=2)
+
+
 def test_stream_frames_delivers_ordered_host_frames():
     from movis_b200 import scenes
     from movis_b200.render import stream_frames
