@@ -8,6 +8,7 @@
 // this file turns mvb_layer records into device records, picks the TMA box of every layer, keeps the
 // cache of TMA descriptors and launches.  Frame and sources are uint8 RGBA HWC in HBM; the frame is
 // written exactly once per launch.
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -66,7 +67,8 @@ struct StackParamsTma {
     StackParams s;
     int32_t stage_bytes;   // bytes of one shared-memory stage (the largest box of this launch)
     int32_t stages_log2;   // 1 or 2: two or four stages in flight
-    int32_t pad_[14];
+    int32_t ux0, uy0, ux1, uy1;   // union of the layers' bboxes, clipped to the frame: tiles outside it are background only
+    int32_t pad_[10];
     alignas(64) CUtensorMap maps[kMaxLayers];
 };
 
@@ -364,6 +366,15 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
                                      4 * kMaxStageBytes + kMaxLayers * 1024);
                 cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
                 smem_dev = dev;
+            }
+            PT.ux0 = W; PT.uy0 = H; PT.ux1 = 0; PT.uy1 = 0;
+            for (int i = 0; i < n; i++) {
+                const DevLayer& L = P.layers[i];
+                if (L.bw <= 0 || L.bh <= 0) continue;
+                PT.ux0 = std::min(PT.ux0, std::max(L.bx, 0));
+                PT.uy0 = std::min(PT.uy0, std::max(L.by, 0));
+                PT.ux1 = std::max(PT.ux1, (int32_t)std::min<int64_t>((int64_t)L.bx + L.bw, W));
+                PT.uy1 = std::max(PT.uy1, (int32_t)std::min<int64_t>((int64_t)L.by + L.bh, H));
             }
             PT.stage_bytes = (stage + 127) & ~127;
             PT.stages_log2 = 4 * PT.stage_bytes <= 36 * 1024 ? 2 : 1;   // keep 3-4 CTAs per SM resident

@@ -139,7 +139,9 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
             // ---- cull + classify: one layer per lane (as in k_stack_opaque) -------------------------
             int cls = -1;
             int2 org = make_int2(0, 0);
-            if (lane < P.n_layers) {
+            // (tiles outside the union of the layers' bboxes take the short way: background only)
+            const bool covered = tx0 < PT.ux1 && tx0 + kTileW > PT.ux0 && ty0 < PT.uy1 && ty0 + kFTileH > PT.uy0;
+            if (covered && lane < P.n_layers) {
                 const int32_t* C = s_cull[lane];
                 const int bx = C[0], by = C[1], bw = C[2], bh = C[3], src_w = C[4], src_h = C[5], box_w = C[6], box_h = C[7];
                 const float m0 = __int_as_float(C[8]), m1 = __int_as_float(C[9]), m2 = __int_as_float(C[10]);
