@@ -160,3 +160,51 @@ def test_reciprocal_table_division_is_exact():
     for d in range(1, 257):
         m = np.uint64(((1 << 24) + d - 1) // d)
         assert np.array_equal(((n << np.uint64(8)) * m) >> np.uint64(32), n // np.uint64(d)), d
+
+
+def test_float_division_constants_of_the_stack_kernel():
+    """movis_b200/csrc/stack_float.cuh divides by 255 with ONE fused multiply-add against the float32
+    constant fl(1/255) = 0x3B808081 (which lies above 1/255):  fma.rm(x, c, 1.5*2^23) leaves
+    floor(x*c) in the low mantissa bits, fma.rn leaves rint(x*c).  Checked here exhaustively over the
+    ranges the kernel uses (the products are exact in float64, like inside an FMA):
+      floor(x * c)   == x // 255             0 <= x <= 65025   (numpy over, multiply, screen)
+      floor(x * 2c)  == 2x // 255            0 <= x <= 65025   (overlay, hard_light, exclusion)
+      rint(x * c)    == (x + 127) // 255     0 <= x <= 65025   (PIL over on an opaque frame)
+    and PIL's own rounding chain equals the closed forms the kernel evaluates."""
+    c = np.float64(np.float32(1.0) / np.float32(255.0))
+    assert np.float32(c).view(np.uint32) == 0x3B808081 and c > 1.0 / 255.0
+    x = np.arange(65026, dtype=np.int64)
+    assert np.array_equal(np.floor(x * c).astype(np.int64), x // 255)
+    assert np.array_equal(np.floor(x * (2 * c)).astype(np.int64), (2 * x) // 255)
+    assert np.array_equal(np.rint(x * c).astype(np.int64), (x + 127) // 255)
+    frac = x * c - np.floor(x * c)
+    assert np.abs(frac - 0.5).min() > 1e-3          # no ties: round-to-nearest is unambiguous
+    # PIL: (((t >> 8) + t) >> 8) >> 7 with t = 128 (x + 128) is floor((x + 127) / 255) ...
+    t = 128 * x + 0x4000
+    assert np.array_equal((((t >> 8) + t) >> 8) >> 7, (x + 127) // 255)
+    # ... and for any t below 2^24 it is (t + (t >> 8)) >> 15; the alpha chain is (u + (u >> 8)) >> 8
+    t = np.arange(0, 255 * 32640 + 0x4000 + 1, dtype=np.int64)
+    assert np.array_equal((((t >> 8) + t) >> 8) >> 7, (t + (t >> 8)) >> 15)
+    u = np.arange(0, 65025 + 0x80 + 1, dtype=np.int64)
+    assert np.array_equal(((u >> 8) + u) >> 8, (u + (u >> 8)) >> 8)
+    # sa == 0 -> coef1 = 0, coef2 = 32640: the formula returns d itself (PIL's "leave the pixel alone")
+    d = np.arange(256, dtype=np.int64)
+    td = d * 32640 + 0x4000
+    assert np.array_equal((td + (td >> 8)) >> 15, d)
+
+
+def test_float_bilinear_of_the_stack_kernel_is_exact():
+    """The horizontal lerp of stack_float.cuh in float32: S = 1024 vl + (32 fx)(vr - vl) + 16384 stays
+    below 2^24 and floor(S / 32768) == (32 vl + fx (vr - vl) + 512) >> 10 for every vertical-lerp value
+    pair on a coarse grid and every fraction (float32 arithmetic emulated with numpy)."""
+    v = np.arange(0, 8161, 37, dtype=np.int64)
+    vl, vr = np.meshgrid(v, v, indexing="ij")
+    for fx in range(32):
+        want = (32 * vl + fx * (vr - vl) + 512) >> 10
+        vlb = np.float32(8388608.0) + vl.astype(np.float32)          # 2^23 + v: what IDP.4A leaves
+        vrb = np.float32(8388608.0) + vr.astype(np.float32)
+        dd = vrb - vlb
+        tt = (vlb.astype(np.float64) * 1024.0 + (16384.0 - 8589934592.0)).astype(np.float32)   # one FMA
+        S = (np.float64(32 * fx) * dd.astype(np.float64) + tt.astype(np.float64)).astype(np.float32)
+        assert np.array_equal(S.astype(np.int64), 1024 * vl + 32 * fx * (vr - vl) + 16384) and S.max() < 2 ** 24
+        assert np.array_equal(np.floor(S.astype(np.float64) / 32768.0).astype(np.int64), want)
