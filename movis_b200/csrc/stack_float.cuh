@@ -350,6 +350,13 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const void* map, int 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
 }
+// a * b + c on the FMA pipe (IMAD), for address arithmetic the compiler would put on the busier ALU pipe
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 {
     uint32_t v;
@@ -407,7 +414,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
         for (int q = 0; q < kFRows; ++q) {
             const int2 r = rowtab[q];
             const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
-            uint32_t a = stage + (uint32_t)(sumy >> 10) * pitch + (uint32_t)(sumx >> 10) * 4u;
+            uint32_t a = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
             if (part) a = (ok >> q & 1) ? a : stage;               // outside the bbox: any valid address; alpha is zeroed below
             t[q][0] = lds_u32(a);
             t[q][1] = lds_u32(a + 4);
