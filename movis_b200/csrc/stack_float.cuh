@@ -21,6 +21,8 @@
 // The tile's pixels stay in registers for the whole layer walk (thread = 1 column x 4 rows).
 #pragma once
 
+#include <type_traits>
+
 #include "pixel_math.cuh"
 
 namespace mvb {
@@ -221,7 +223,6 @@ struct RowPairState { u64 c[4]; };   // r, g, b, a of rows (2p, 2p+1), biased (a
 // serves all of it (offsets become LDS immediates).
 struct __align__(16) SlotMem {
     int4 info;               // see the table-building code
-    int4 box;                // bbox (x, y, w, h), for tiles the layer covers only partly
     int2 col[kTileW];        // (adelta, bdelta) per tile column
     int2 row[kFTileH];       // (X0, Y0) per tile row (relative to the box origin for TMA layers)
     float lut[256];          // opacity-scaled alpha, as float
@@ -364,7 +365,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
     return v;
 }
 
-enum { kTileTma = 3 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
+enum { kTileTma = 3, kTileTmaPart = 7 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
 
 // What identifies a thread's pixels inside the tile being walked.
 struct PixelCtx {
@@ -386,8 +387,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
     const bool x_ok = C.x_ok;
     (void)tx0;
     const int4 info = S.info;
-    const int cls = (info.x >> 8) & 3;
-    const bool part = info.x & (1 << 10);
+    const int cls = (info.x >> 8) & 7;
     const int2 col = S.col[lane];
     const int2* __restrict__ rowtab = &S.row[rbeg];
 
@@ -396,33 +396,41 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
     float fxs[kFRows];
     uint32_t wy[kFRows];
     unsigned ok = 0xFu;   // bit q: row q of this thread lies inside the layer's bbox and the frame
-    if (cls == kTileTma) {
+    if ((cls & 3) == kTileTma) {
         before_tma_wait(info);
         const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
-        if (part) {
-            const int4 bb = S.box;
-            const bool col_in = x_ok && (unsigned)(x - bb.x) < (unsigned)bb.z;
-            ok = 0;
+        // Tiles the bbox covers only partly run their own copy of the loop (cls == kTileTmaPart): the box
+        // spans the covered part alone, so samples outside it read a dummy address with weight 0, which
+        // makes them transparent (alpha 0 -> lut[0] = 0).  Fully covered tiles carry none of that.
+        auto fetch = [&](auto part_tag) {
+            constexpr bool PART = decltype(part_tag)::value;
+            if (PART) {
+                const DevLayer& L = P.layers[layer_index];
+                const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
+                ok = 0u;
+#pragma unroll
+                for (int q = 0; q < kFRows; ++q) {
+                    const int yy = ty0 + rbeg + q;
+                    if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) ok |= 1u << q;
+                }
+            }
+            mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
 #pragma unroll
             for (int q = 0; q < kFRows; ++q) {
-                const int yy = ty0 + rbeg + q;
-                ok |= (col_in && (unsigned)(yy - bb.y) < (unsigned)bb.w && yy < P.H) ? (1u << q) : 0u;
+                const int2 r = rowtab[q];
+                const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
+                uint32_t a = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
+                wy[q] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;     // bytes (32 - fy, fy, 0, 0)
+                if (PART && !(ok >> q & 1)) { a = stage; wy[q] = 0u; }
+                t[q][0] = lds_u32(a);
+                t[q][1] = lds_u32(a + 4);
+                t[q][2] = lds_u32(a + pitch);
+                t[q][3] = lds_u32(a + pitch + 4);
+                fxs[q] = (float)(sumx & 0x3E0);                        // 32 * fx
             }
-        }
-        mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
-#pragma unroll
-        for (int q = 0; q < kFRows; ++q) {
-            const int2 r = rowtab[q];
-            const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
-            uint32_t a = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
-            if (part) a = (ok >> q & 1) ? a : stage;               // outside the bbox: any valid address; alpha is zeroed below
-            t[q][0] = lds_u32(a);
-            t[q][1] = lds_u32(a + 4);
-            t[q][2] = lds_u32(a + pitch);
-            t[q][3] = lds_u32(a + pitch + 4);
-            fxs[q] = (float)(sumx & 0x3E0);                        // 32 * fx
-            wy[q] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;     // bytes (32 - fy, fy, 0, 0)
-        }
+        };
+        if (cls == kTileTma) fetch(std::false_type{});
+        else fetch(std::true_type{});
         __syncwarp();
         if (lane == 0) mbar_arrive((uint32_t)info.y + 32);         // this warp is done with the stage
     } else if (cls == kTileInterior) {
@@ -497,11 +505,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
         }
         float a0, a1;
         upk(s[p][3], a0, a1);
-        uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);
-        if (part) {   // rows outside the bbox sampled a dummy address: alpha 0 -> lut[0] = 0 -> no-op
-            i0 = (ok >> (2 * p) & 1) ? i0 : kMagicBits;
-            i1 = (ok >> (2 * p + 1) & 1) ? i1 : kMagicBits;
-        }
+        const uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);
         fa[p] = pk(lds_f32(lut_base + (i0 << 2)), lds_f32(lut_base + (i1 << 2)));
     }
 
@@ -590,7 +594,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
                     // the box to start on a 16-byte boundary of the row: x origin a multiple of 4 px
                     const int fx0 = ((int)floorf(xmin) - 1) & ~3, fy0 = (int)floorf(ymin) - 1;
                     if (box_w > 0 && (int)floorf(xmax) + 3 - fx0 <= box_w && (int)floorf(ymax) + 3 - fy0 <= box_h) {
-                        cls = kTileTma | (full ? 0 : 256);
+                        cls = full ? kTileTma : kTileTmaPart;
                         org = make_int2(fx0, fy0);
                     } else if (full && xmin > 0.25f && xmax < src_w - 1.25f && ymin > 0.25f && ymax < src_h - 1.25f) {
                         cls = kTileInterior;   // whole tile covered and every tap inside the source
@@ -627,7 +631,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
     // every warp derives the paint-ordered list of active layers from the class table by itself
     const int my_cls = s_class[lane];
     const unsigned m_act = __ballot_sync(0xFFFFFFFFu, my_cls >= 0);
-    const unsigned m_tma = __ballot_sync(0xFFFFFFFFu, my_cls >= 0 && (my_cls & 255) == kTileTma);
+    const unsigned m_tma = __ballot_sync(0xFFFFFFFFu, my_cls >= 0 && (my_cls & 3) == kTileTma);
     const int n_active = __popc(m_act);
     const int n_tma = __popc(m_tma);
 
@@ -664,17 +668,16 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
             const int li = nth_set_bit(m_rest, tid);
             const DevLayer& L = P.layers[li];
             const int cls = s_class[li];
-            const int k = (cls & 255) == kTileTma ? __popc(m_tma & ((1u << li) - 1u)) : 0;
-            // x: mode (8 bits) | class (2) | partial coverage (bit 10) | phase parity (bit 11) |
+            const int k = (cls & 3) == kTileTma ? __popc(m_tma & ((1u << li) - 1u)) : 0;
+            // x: mode (8 bits) | class (3) | phase parity (bit 11) |
             //    refill: thread 0 re-arms the stage of TMA layer k-1 before this layer (bit 12) | row pitch << 16
             // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]   w: stage address
             const int refill = k >= 1 && k + ns_mask < n_tma;
-            s_slot[tid].info = make_int4((L.pil ? kPilOver : L.mode) | ((cls & 3) << 8) | ((cls >> 8) << 10) |
+            s_slot[tid].info = make_int4((L.pil ? kPilOver : L.mode) | ((cls & 7) << 8) |
                                         (((k >> ns_log2) & 1) << 11) | (refill << 12) | ((L.box_w * 4) << 16),
                                     (int)(bar_full + 8 * (k & ns_mask)),
                                     (int)(smem_addr(s_slot[tid].lut) - (kMagicBits << 2)),
                                     (int)(stage0 + (k & ns_mask) * PT.stage_bytes));
-            s_slot[tid].box = make_int4(L.bx, L.by, L.bw, L.bh);
             s_layer[tid] = li | (k << 8);
         }
         for (int slot = 0; slot < n_here; ++slot, m_rest &= m_rest - 1) {   // 256 threads: one LUT entry each

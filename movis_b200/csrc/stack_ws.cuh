@@ -31,7 +31,6 @@ constexpr int kWsUnits = 4;                       // unit buffers: how far the p
 // Per layer of a unit: as SlotMem, without the alpha LUT (one per layer per CTA here, see s_lut).
 struct __align__(16) UnitSlot {
     int4 info;
-    int4 box;
     int2 col[kTileW];
     int2 row[kFTileH];
 };
@@ -162,7 +161,7 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                         cls = kTileEdge;
                         const int fx0 = ((int)floorf(xmin) - 1) & ~3, fy0 = (int)floorf(ymin) - 1;
                         if (box_w > 0 && (int)floorf(xmax) + 3 - fx0 <= box_w && (int)floorf(ymax) + 3 - fy0 <= box_h) {
-                            cls = kTileTma | (full ? 0 : 256);
+                            cls = full ? kTileTma : kTileTmaPart;
                             org = make_int2(fx0, fy0);
                         } else if (full && xmin > 0.25f && xmax < src_w - 1.25f && ymin > 0.25f && ymax < src_h - 1.25f) {
                             cls = kTileInterior;
@@ -179,7 +178,7 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                 if (lane < n_here) my_li = nth_set_bit(rest, lane);
                 const int my_c = __shfl_sync(0xFFFFFFFFu, cls, my_li);
                 const int2 my_org = make_int2(__shfl_sync(0xFFFFFFFFu, org.x, my_li), __shfl_sync(0xFFFFFFFFu, org.y, my_li));
-                const unsigned want = __ballot_sync(0xFFFFFFFFu, lane < n_here && (my_c & 255) == kTileTma);
+                const unsigned want = __ballot_sync(0xFFFFFFFFu, lane < n_here && (my_c & 3) == kTileTma);
                 const int my_g = g + __popc(want & ((1u << lane) - 1u));
                 for (int i = 0; i < n_here; ++i) rest &= rest - 1;
 
@@ -205,14 +204,13 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                     S.col[lane] = make_int2(warp_adelta(L.m, tx0 + lane - L.bx), warp_bdelta(L.m, tx0 + lane - L.bx));
                     S.row[lane] = make_int2(warp_x0(L.m, ty0 + lane - L.by) - ox * 1024, warp_y0(L.m, ty0 + lane - L.by) - oy * 1024);
                     if (lane == 0) {
-                        // x: mode (8 bits) | class (2) | partial coverage (bit 10) | phase parity (bit 11) | row pitch << 16
+                        // x: mode (8 bits) | class (3) | phase parity (bit 11) | row pitch << 16
                         // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]   w: stage address
-                        S.info = make_int4((L.pil ? kPilOver : L.mode) | ((c & 3) << 8) | ((c >> 8) << 10) |
+                        S.info = make_int4((L.pil ? kPilOver : L.mode) | ((c & 7) << 8) |
                                                (((gq >> ns_log2) & 1) << 11) | ((L.box_w * 4) << 16),
                                            (int)(bar_full + 8 * (gq & ns_mask)),
                                            (int)(smem_addr(s_lut + li * 256) - (kMagicBits << 2)),
                                            (int)(stage0 + (gq & ns_mask) * PT.stage_bytes));
-                        S.box = make_int4(L.bx, L.by, L.bw, L.bh);
                         U.layer[slot] = li;
                     }
                 }
