@@ -367,6 +367,17 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 
 enum { kTileTma = 3, kTileTmaPart = 7 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
 
+// cv2's bilinear weights of a sample at (sumx, sumy) (1/1024 px; 5 fractional bits are used):
+// wt = (32 - fx)(32 - fy) | fx (32 - fy) << 16,  wb = (32 - fx) fy | fx fy << 16  (imgwarp.cpp: the
+// INTER_LINEAR table of initInterTab2D, whose entries are these exact products).
+__device__ __forceinline__ void tap_weights(int sumx, int sumy, uint32_t& wt, uint32_t& wb)
+{
+    const uint32_t fx = (uint32_t)(sumx >> 5) & 31u, fy = (uint32_t)(sumy >> 5) & 31u;
+    const uint32_t a = imad(fx, 0xFFFFu, 32u);   // (32 - fx) | fx << 16
+    wb = a * fy;
+    wt = (a << 5) - wb;
+}
+
 // What identifies a thread's pixels inside the tile being walked.
 struct PixelCtx {
     int tx0, ty0;   // tile origin in the frame
@@ -393,8 +404,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
 
     // ---- taps of the four rows, all requested before the first is used ----------------------
     uint32_t t[kFRows][4];
-    float fxs[kFRows];
-    uint32_t wy[kFRows];
+    uint32_t wt[kFRows], wb[kFRows];   // cv2's 2 x 2 weights, two 16-bit values each: (w00, w01), (w10, w11)
     unsigned ok = 0xFu;   // bit q: row q of this thread lies inside the layer's bbox and the frame
     if ((cls & 3) == kTileTma) {
         before_tma_wait(info);
@@ -420,13 +430,12 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
                 const int2 r = rowtab[q];
                 const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
                 uint32_t a = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
-                wy[q] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;     // bytes (32 - fy, fy, 0, 0)
-                if (PART && !(ok >> q & 1)) { a = stage; wy[q] = 0u; }
+                tap_weights(sumx, sumy, wt[q], wb[q]);
+                if (PART && !(ok >> q & 1)) { a = stage; wt[q] = wb[q] = 0u; }
                 t[q][0] = lds_u32(a);
                 t[q][1] = lds_u32(a + 4);
                 t[q][2] = lds_u32(a + pitch);
                 t[q][3] = lds_u32(a + pitch + 4);
-                fxs[q] = (float)(sumx & 0x3E0);                        // 32 * fx
             }
         };
         if (cls == kTileTma) fetch(std::false_type{});
@@ -446,8 +455,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
             t[k][1] = ldg_u32(p + 4);
             t[k][2] = ldg_u32(p + ss);
             t[k][3] = ldg_u32(p + ss + 4);
-            fxs[k] = (float)(sumx & 0x3E0);
-            wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
+            tap_weights(sumx, sumy, wt[k], wb[k]);
         }
     } else {
         const DevLayer& L = P.layers[layer_index];
@@ -467,42 +475,33 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
             } else {
                 ok &= ~(1u << k);
             }
-            fxs[k] = (float)(sumx & 0x3E0);
-            wy[k] = (uint32_t)((sumy >> 5) & 31) * 255u + 32u;
+            tap_weights(sumx, sumy, wt[k], wb[k]);
         }
     }
 
     // ---- cv2's fixed-point bilinear: out = (sum w p + 512) >> 10 -------------------------------
+    // IDP.2A multiplies the two 16-bit weights of a tap row with two bytes: with the taps of a row paired
+    // by channel, four of them give one channel's exact sum; started from the bits of 2^23 + 512 the
+    // accumulator IS the float 2^23 + 512 + sum, and one fma.rm takes floor(. / 1024) of a row pair.
     u64 s[2][4], fa[2];
     // &lut[bits - kMagicBits] for the biased alpha `bits`: one LEA (the shift drops the exponent bits)
     const uint32_t lut_base = (uint32_t)info.z;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        float vl[2][4], vr[2][4];
+        float v[2][4];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int k = 2 * p + q;
-            const uint32_t wa = wy[k], wb = wy[k] << 16;
-            const uint32_t l_rg = __byte_perm(t[k][0], t[k][2], 0x5140), l_ba = __byte_perm(t[k][0], t[k][2], 0x7362);
-            const uint32_t r_rg = __byte_perm(t[k][1], t[k][3], 0x5140), r_ba = __byte_perm(t[k][1], t[k][3], 0x7362);
-            vl[q][0] = __uint_as_float(__dp4a(l_rg, wa, kTwo23Bits));   // 2^23 + p00 (32 - fy) + p10 fy
-            vl[q][1] = __uint_as_float(__dp4a(l_rg, wb, kTwo23Bits));
-            vl[q][2] = __uint_as_float(__dp4a(l_ba, wa, kTwo23Bits));
-            vl[q][3] = __uint_as_float(__dp4a(l_ba, wb, kTwo23Bits));
-            vr[q][0] = __uint_as_float(__dp4a(r_rg, wa, kTwo23Bits));
-            vr[q][1] = __uint_as_float(__dp4a(r_rg, wb, kTwo23Bits));
-            vr[q][2] = __uint_as_float(__dp4a(r_ba, wa, kTwo23Bits));
-            vr[q][3] = __uint_as_float(__dp4a(r_ba, wb, kTwo23Bits));
+            const uint32_t t_rg = __byte_perm(t[k][0], t[k][1], 0x5140), t_ba = __byte_perm(t[k][0], t[k][1], 0x7362);
+            const uint32_t b_rg = __byte_perm(t[k][2], t[k][3], 0x5140), b_ba = __byte_perm(t[k][2], t[k][3], 0x7362);
+            v[q][0] = __uint_as_float(__dp2a_lo(wb[k], b_rg, __dp2a_lo(wt[k], t_rg, kTwo23Bits + 512u)));
+            v[q][1] = __uint_as_float(__dp2a_hi(wb[k], b_rg, __dp2a_hi(wt[k], t_rg, kTwo23Bits + 512u)));
+            v[q][2] = __uint_as_float(__dp2a_lo(wb[k], b_ba, __dp2a_lo(wt[k], t_ba, kTwo23Bits + 512u)));
+            v[q][3] = __uint_as_float(__dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, kTwo23Bits + 512u)));
         }
-        const u64 fx2 = pk(fxs[2 * p], fxs[2 * p + 1]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            // 32 (32 vl + fx (vr - vl) + 512) = 1024 vl + (32 fx)(vr - vl) + 16384  < 2^24
-            const u64 vl2 = pk(vl[0][c], vl[1][c]);
-            const u64 dd = sub2(pk(vr[0][c], vr[1][c]), vl2);
-            const u64 tt = fma2(vl2, bc(1024.0f), bc(16384.0f - 8589934592.0f));
-            s[p][c] = fma2_rm(fma2(fx2, dd, tt), bc(1.0f / 32768.0f), bc(kMagic));
-        }
+        for (int c = 0; c < 4; ++c)   // (2^23 + 512 + sum) / 1024 = 8192 + (sum + 512) / 1024
+            s[p][c] = fma2_rm(pk(v[0][c], v[1][c]), bc(1.0f / 1024.0f), bc(kMagic - 8192.0f));
         float a0, a1;
         upk(s[p][3], a0, a1);
         const uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);

@@ -194,17 +194,22 @@ def test_float_division_constants_of_the_stack_kernel():
 
 
 def test_float_bilinear_of_the_stack_kernel_is_exact():
-    """The horizontal lerp of stack_float.cuh in float32: S = 1024 vl + (32 fx)(vr - vl) + 16384 stays
-    below 2^24 and floor(S / 32768) == (32 vl + fx (vr - vl) + 512) >> 10 for every vertical-lerp value
-    pair on a coarse grid and every fraction (float32 arithmetic emulated with numpy)."""
-    v = np.arange(0, 8161, 37, dtype=np.int64)
-    vl, vr = np.meshgrid(v, v, indexing="ij")
+    """The bilinear step of stack_float.cuh: the 2 x 2 weights are the exact products (32 - fx)(32 - fy)...
+    packed as 16-bit pairs by two integer multiplies without carries between the halves, the IDP.2A sum
+    started at the bits of 2^23 + 512 is the float 2^23 + 512 + sum (< 2^24), and one fma rounded down,
+    X * 2^-10 + (1.5 * 2^23 - 8192), leaves 1.5 * 2^23 + ((sum + 512) >> 10): cv2's result."""
     for fx in range(32):
-        want = (32 * vl + fx * (vr - vl) + 512) >> 10
-        vlb = np.float32(8388608.0) + vl.astype(np.float32)          # 2^23 + v: what IDP.4A leaves
-        vrb = np.float32(8388608.0) + vr.astype(np.float32)
-        dd = vrb - vlb
-        tt = (vlb.astype(np.float64) * 1024.0 + (16384.0 - 8589934592.0)).astype(np.float32)   # one FMA
-        S = (np.float64(32 * fx) * dd.astype(np.float64) + tt.astype(np.float64)).astype(np.float32)
-        assert np.array_equal(S.astype(np.int64), 1024 * vl + 32 * fx * (vr - vl) + 16384) and S.max() < 2 ** 24
-        assert np.array_equal(np.floor(S.astype(np.float64) / 32768.0).astype(np.int64), want)
+        for fy in range(32):
+            a = (fx * 0xFFFF + 32) & 0xFFFFFFFF
+            wb = (a * fy) & 0xFFFFFFFF
+            wt = ((a << 5) - wb) & 0xFFFFFFFF
+            assert (wt & 0xFFFF, wt >> 16) == ((32 - fx) * (32 - fy), fx * (32 - fy))
+            assert (wb & 0xFFFF, wb >> 16) == ((32 - fx) * fy, fx * fy)
+    sums = np.arange(0, 255 * 1024 + 1, dtype=np.int64)                    # every possible weighted sum
+    bits = (np.uint32(0x4B000000 + 512) + sums.astype(np.uint32))
+    X = bits.view(np.float32)
+    assert np.array_equal(X.astype(np.int64), (1 << 23) + 512 + sums) and X.max() < 2 ** 24
+    exact = X.astype(np.float64) / 1024.0 + (12582912.0 - 8192.0)          # the fma before its one rounding
+    down = np.floor(exact)                                                 # ulp is 1 in [2^23, 2^24): fma.rm = floor
+    assert down.max() < 2 ** 24 and np.array_equal(down.astype(np.float32).astype(np.float64), down)
+    assert np.array_equal(down.astype(np.int64) - 12582912, (sums + 512) >> 10)
