@@ -206,9 +206,14 @@ def run_product(args) -> dict:
             src[odd & (src == p)] = twins[i].data_ptr()
         return plan
 
+    CHUNK = 30   # frames planned per host call, as Composition.render_frames does it (even: keeps the twin parity)
+
     def step():
-        plan = alternate(plan_range(comp, times))   # host: batched keyframes + affine set-up
-        launch_plan(plan, frames, bg)               # device: one fused launch per frame
+        # host: batched keyframes + affine set-up of a chunk; device: the fused launches of the chunk
+        # before it, so only the first chunk after an idle device is not overlapped
+        for i in range(0, FRAMES_PER_STEP, CHUNK):
+            plan = alternate(plan_range(comp, times[i:i + CHUNK]))
+            launch_plan(plan, frames[i:i + CHUNK], bg)
         return plan
 
     for _ in range(max(args.warmup, 3)):
@@ -228,7 +233,7 @@ def run_product(args) -> dict:
     clocks = sampler.stop() if rank == 0 else {}
     total_frames = world * args.steps * FRAMES_PER_STEP
     value = total_frames / elapsed
-    launches = args.steps * FRAMES_PER_STEP
+    launches = args.steps * FRAMES_PER_STEP * 2   # per frame: k_stack_tables (cv2 tables) + k_stack_ws
 
     # --- roofline of the fused kernel: launches only, plan prebuilt, CUDA events on the launch stream
     plan = alternate(plan_range(comp, times))

@@ -68,8 +68,20 @@ struct StackParamsTma {
     int32_t stage_bytes;   // bytes of one shared-memory stage (the largest box of this launch)
     int32_t stages_log2;   // 1 or 2: two or four stages in flight
     int32_t ux0, uy0, ux1, uy1;   // union of the layers' bboxes, clipped to the frame: tiles outside it are background only
-    int32_t pad_[10];
+    // cv2's integer tables of every layer for the whole frame (k_stack_tables): per layer tab_w entries
+    // (adelta, bdelta) by frame column, then tab_h entries (X0, Y0) by frame row; both padded to tiles
+    const int2* tab;
+    int32_t tab_w, tab_h;
+    int32_t pad_[6];
     alignas(64) CUtensorMap maps[kMaxLayers];
+};
+
+// Parameters of k_stack_tables: what cv::warpAffine's table set-up needs of each layer.
+struct TableLayer { double m[6]; int32_t bx, by; };
+struct TableParams {
+    int2* tab;
+    int32_t tab_w, tab_h, n_layers, pad_;
+    TableLayer l[kMaxLayers];
 };
 
 constexpr int kPilOver = 18; // dispatch code of PIL's "over" next to the 18 numpy blend modes
@@ -312,6 +324,29 @@ static bool tensor_map_for(const DevLayer& L, CUtensorMap* out)
     return true;
 }
 
+// Device scratch for the tables of one launch, one buffer per (device, stream), grown on demand and kept.
+// (cudaMallocAsync was tried: its pool trims at every synchronisation and re-allocating stalls the stream.)
+static void* table_scratch(cudaStream_t stream, size_t bytes)
+{
+    struct Buf { void* p; size_t cap; };
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, Buf> bufs;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t key = ((uint64_t)(uintptr_t)stream << 6) ^ (uint64_t)dev;
+    std::lock_guard<std::mutex> lock(mu);
+    Buf& b = bufs[key];
+    if (b.cap < bytes) {
+        if (b.p) cudaFree(b.p);   // synchronises: nothing in flight reads the old buffer afterwards
+        b.p = nullptr;
+        b.cap = 0;
+        const size_t cap = std::max<size_t>(bytes, (size_t)1 << 20);
+        if (cudaMalloc(&b.p, cap) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return nullptr; }
+        b.cap = cap;
+    }
+    return b.p;
+}
+
 static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t bg[4], int n_layers,
                         const mvb_layer* layers, int flags, cudaStream_t stream)
 {
@@ -384,8 +419,38 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
                 const int n_tiles = (int)(grid.x * grid.y);
                 const int ctas = n_tiles < 3 * n_sm ? n_tiles : 3 * n_sm;
                 const size_t smem = ((size_t)PT.stage_bytes << PT.stages_log2) + (size_t)n * 1024;
-                if (opaque) k_stack_ws<true><<<ctas, kWsThreads, smem, stream>>>(PT);
-                else k_stack_ws<false><<<ctas, kWsThreads, smem, stream>>>(PT);
+                // cv2's tables for the whole frame, once per launch (scratch owned by the stream: launches on a
+                // stream are ordered, so the next frame's tables cannot overtake this frame's walk)
+                static thread_local TableParams TP;
+                TP.tab_w = PT.tab_w = (int32_t)grid.x * kTileW;
+                TP.tab_h = PT.tab_h = (int32_t)grid.y * kFTileH;
+                TP.n_layers = n;
+                for (int i = 0; i < n; i++) {
+                    std::memcpy(TP.l[i].m, P.layers[i].m, sizeof(TP.l[i].m));
+                    TP.l[i].bx = P.layers[i].bx;
+                    TP.l[i].by = P.layers[i].by;
+                }
+                const size_t tab_bytes = (size_t)(n > 0 ? n : 1) * (size_t)(TP.tab_w + TP.tab_h) * sizeof(int2);
+                void* tab = table_scratch(stream, tab_bytes);
+                if (!tab) return set_error(MVB_ERR_CUDA, "no device memory for the warp tables");
+                TP.tab = static_cast<int2*>(tab);
+                PT.tab = TP.tab;
+                if (n > 0) k_stack_tables<<<dim3((unsigned)((TP.tab_w + TP.tab_h + 255) / 256), (unsigned)n), 256, 0, stream>>>(TP);
+                // Programmatic dependent launch: the stack kernel's CTAs may start their prologue (barriers,
+                // opacity LUTs) while the tables kernel drains; its producer warps wait for the tables
+                // (griddepcontrol.wait) before they copy the first one.
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)ctas);
+                cfg.blockDim = dim3(kWsThreads);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = n > 0 ? 1 : 0;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                if (opaque) cudaLaunchKernelEx(&cfg, k_stack_ws<true>, PT);
+                else cudaLaunchKernelEx(&cfg, k_stack_ws<false>, PT);
             }
         }
         done += n;

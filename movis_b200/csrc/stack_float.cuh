@@ -410,7 +410,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
         before_tma_wait(info);
         const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
         // Tiles the bbox covers only partly run their own copy of the loop (cls == kTileTmaPart): the box
-        // spans the covered part alone, so samples outside it read a dummy address with weight 0, which
+        // spans the covered part alone, so samples outside it read a dummy address (softg) with weight 0, which
         // makes them transparent (alpha 0 -> lut[0] = 0).  Fully covered tiles carry none of that.
         auto fetch = [&](auto part_tag) {
             constexpr bool PART = decltype(part_tag)::value;
@@ -431,11 +431,12 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
                 const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
                 uint32_t a = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
                 tap_weights(sumx, sumy, wt[q], wb[q]);
-                if (PART && !(ok >> q & 1)) { a = stage; wt[q] = wb[q] = 0u; }
+                uint32_t down = pitch;
+                if (PART && !(ok >> q & 1)) { a = smem_addr(softg); down = 0u; wt[q] = wb[q] = 0u; }
                 t[q][0] = lds_u32(a);
                 t[q][1] = lds_u32(a + 4);
-                t[q][2] = lds_u32(a + pitch);
-                t[q][3] = lds_u32(a + pitch + 4);
+                t[q][2] = lds_u32(a + down);
+                t[q][3] = lds_u32(a + down + 4);
             }
         };
         if (cls == kTileTma) fetch(std::false_type{});

@@ -41,6 +41,33 @@ struct __align__(16) UnitMem {
     UnitSlot slot[kWsSlots];
 };
 
+// cv::warpAffine's integer tables (imgwarp.cpp: adelta / bdelta by destination column, X0 / Y0 by
+// destination row; fp64 without FMA contraction, see pixel_math.cuh) of every layer of a launch for the
+// whole frame.  They depend on the layer and the frame column / row only, so they are built once per
+// launch instead of once per tile; the producer warp of k_stack_ws copies a tile's 2 x 256 bytes per
+// layer into shared memory with cp.async.bulk.
+__global__ void __launch_bounds__(256)
+k_stack_tables(const __grid_constant__ TableParams T)
+{
+    asm volatile("griddepcontrol.launch_dependents;");   // k_stack_ws may start its prologue now
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const TableLayer& L = T.l[blockIdx.y];
+    int2* out = T.tab + (size_t)blockIdx.y * (size_t)(T.tab_w + T.tab_h);
+    if (i < T.tab_w) {
+        out[i] = make_int2(warp_adelta(L.m, i - L.bx), warp_bdelta(L.m, i - L.bx));
+    } else if (i < T.tab_w + T.tab_h) {
+        const int v = i - T.tab_w - L.by;
+        out[i] = make_int2(warp_x0(L.m, v), warp_y0(L.m, v));
+    }
+}
+
+// 1-D bulk copy global -> shared memory, completion signalled on `bar` in bytes (16-byte granular).
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // OPAQUE: the frame's alpha is 255 throughout (opaque bg_color); otherwise alpha is carried as a
 // fourth channel and both "over" operators use their general forms (over_numpy_rows / over_pil_rows).
 template <bool OPAQUE>
@@ -104,6 +131,7 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
         // building of the next unit, which is what the consumers run out of first.
         int head = 0;   // next request number to issue
         int q_li = 0, q_ox = 0, q_oy = 0;
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // the tables of k_stack_tables are complete and visible
         auto service = [&]() {
             while (head < g) {
                 const int st = head & ns_mask;
@@ -194,30 +222,32 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                 }
                 g += __popc(want);
                 service();
-                for (int slot = 0; slot < n_here; ++slot) {
-                    const int li = __shfl_sync(0xFFFFFFFFu, my_li, slot), c = __shfl_sync(0xFFFFFFFFu, my_c, slot);
-                    const int ox = __shfl_sync(0xFFFFFFFFu, my_org.x, slot), oy = __shfl_sync(0xFFFFFFFFu, my_org.y, slot);
-                    const int gq = __shfl_sync(0xFFFFFFFFu, my_g, slot);
-                    const DevLayer& L = P.layers[li];
-                    UnitSlot& S = U.slot[slot];
-                    // cv::warpAffine's tables restricted to the tile: lane = column, then lane = row
-                    S.col[lane] = make_int2(warp_adelta(L.m, tx0 + lane - L.bx), warp_bdelta(L.m, tx0 + lane - L.bx));
-                    S.row[lane] = make_int2(warp_x0(L.m, ty0 + lane - L.by) - ox * 1024, warp_y0(L.m, ty0 + lane - L.by) - oy * 1024);
-                    if (lane == 0) {
-                        // x: mode (8 bits) | class (3) | phase parity (bit 11) | row pitch << 16
-                        // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]   w: stage address
-                        S.info = make_int4((L.pil ? kPilOver : L.mode) | ((c & 7) << 8) |
-                                               (((gq >> ns_log2) & 1) << 11) | ((L.box_w * 4) << 16),
-                                           (int)(bar_full + 8 * (gq & ns_mask)),
-                                           (int)(smem_addr(s_lut + li * 256) - (kMagicBits << 2)),
-                                           (int)(stage0 + (gq & ns_mask) * PT.stage_bytes));
-                        U.layer[slot] = li;
-                    }
+                // lane s < n_here fills slot s: the info word, and two bulk copies of the layer's tables
+                // restricted to the tile (columns tx0.., rows ty0..), which complete on the unit's barrier
+                const uint32_t ubar = unit_full + 8 * (u & (kWsUnits - 1));
+                if (lane == 0) U.hdr = make_int4(tx0, ty0, n_here | (first ? 256 : 0) | (rest == 0 ? 512 : 0), 0);
+                if (lane < n_here) {
+                    const int32_t* C = s_cull[my_li];
+                    const int pitch = C[6] * 4;   // box_w px
+                    UnitSlot& S = U.slot[lane];
+                    // x: mode (8 bits) | class (3) | phase parity (bit 11) | row pitch << 16
+                    // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]
+                    // w: address the stage would have at source pixel (0, 0): stage - origin
+                    S.info = make_int4((C[15] ? kPilOver : C[14]) | ((my_c & 7) << 8) |
+                                           (((my_g >> ns_log2) & 1) << 11) | (pitch << 16),
+                                       (int)(bar_full + 8 * (my_g & ns_mask)),
+                                       (int)(smem_addr(s_lut + my_li * 256) - (kMagicBits << 2)),
+                                       (int)(stage0 + (my_g & ns_mask) * PT.stage_bytes - my_org.y * pitch - my_org.x * 4));
+                    U.layer[lane] = my_li;
+                    const int2* tab = PT.tab + (size_t)my_li * (size_t)(PT.tab_w + PT.tab_h);
+                    bulk_load(smem_addr(S.col), tab + tx0, sizeof(int2) * kTileW, ubar);
+                    bulk_load(smem_addr(S.row), tab + PT.tab_w + ty0, sizeof(int2) * kFTileH, ubar);
                 }
-                const bool last = rest == 0;
-                if (lane == 0) U.hdr = make_int4(tx0, ty0, n_here | (first ? 256 : 0) | (last ? 512 : 0), 0);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(unit_full + 8 * (u & (kWsUnits - 1)));   // publish (release: the warp's writes above)
+                if (lane == 0) {   // publish (release: the warp's writes above); the phase ends when the copies have landed
+                    if (n_here) mbar_arrive_expect_tx(ubar, (uint32_t)n_here * (uint32_t)(sizeof(int2) * (kTileW + kFTileH)));
+                    else mbar_arrive(ubar);
+                }
                 service();
                 ++u;
                 first = false;
