@@ -111,6 +111,9 @@ typedef struct mvb_layer {
  * tile walks the layer stack in registers; the frame is written once).
  * `layers` is a HOST array.  Results are bit-identical to running the reference's
  * warpAffine -> alpha_composite pair per layer.
+ * The library keeps a small device scratch buffer per (device, stream) for cv2's coordinate tables
+ * (8 bytes x (width + height) per layer); calls that share a stream must not be made concurrently
+ * from several host threads.
  */
 MVB_API int mvb_composite_stack(void* frame, int32_t frame_w, int32_t frame_h, int64_t frame_stride,
                         const uint8_t bg_color[4], int32_t n_layers, const mvb_layer* layers,
