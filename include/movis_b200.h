@@ -196,6 +196,15 @@ MVB_API int mvb_effect_chroma_key_rgba8(const void* src, int32_t w, int32_t h, i
 MVB_API int mvb_effect_fill_color_rgba8(const void* src, int32_t w, int32_t h, int64_t src_stride, void* dst,
                                 int64_t dst_stride, const uint8_t color[3], mvb_stream_t stream);
 
+/* Stripe.__call__ (movis/layer/texture.py:159-191): the procedural stripe image, evaluated with the
+ * reference's float64 operations in the reference's order (bit-identical pixels).  `params` is a HOST
+ * array of 16 doubles: sin(theta), cos(theta), height / 2, width / 2, total_width, phase,
+ * edge0 = max(ratio - 0.01, 0), edge1 - edge0 with edge1 = min(ratio + 0.01, 1), then the two RGBA
+ * colours as the reference rounds them (np.round(color), np.round(255 * opacity)).
+ * solid = 1 / 2: the reference's early returns for ratio <= 0 / ratio >= 1 (all colour 1 / colour 2). */
+MVB_API int mvb_source_stripe_rgba8(void* dst, int32_t w, int32_t h, int64_t dst_stride, const double params[16],
+                            int32_t solid, mvb_stream_t stream);
+
 /* HSLShift.__call__ (movis/effect/color.py:56-69).  The three float32 remaps of color.py:64-66
  * are passed as host 256-entry tables (evaluated by the caller with numpy, so their rounding is
  * numpy's own); RGB->HSV and HSV->RGB follow cv2's 8-bit arithmetic, including the different

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "mvb_blur_ksize", "mvb_gaussian_weights_q8", "mvb_effect_blur_scratch_bytes",
     "mvb_effect_blur_rgba8", "mvb_effect_drop_shadow_rgba8", "mvb_effect_chroma_key_rgba8",
     "mvb_effect_fill_color_rgba8", "mvb_effect_hsl_shift_rgba8", "mvb_rgb_to_hsv_u8",
+    "mvb_source_stripe_rgba8",
 ]
 
 
@@ -75,6 +76,7 @@ def lib():
     L.mvb_effect_fill_color_rgba8.argtypes = [vp, i32, i32, i64, vp, i64, vp, vp]
     L.mvb_effect_hsl_shift_rgba8.argtypes = [vp, i32, i32, i64, vp, i64, vp, vp, vp, vp]
     L.mvb_rgb_to_hsv_u8.argtypes = [vp, vp]
+    L.mvb_source_stripe_rgba8.argtypes = [vp, i32, i32, i64, vp, i32, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:  # default restype: our int-returning calls

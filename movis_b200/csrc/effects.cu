@@ -687,6 +687,74 @@ extern "C" int mvb_effect_hsl_shift_rgba8(const void* src, int32_t w, int32_t h,
     return launch_pointwise(P, src, w, h, sstride, dst, dstride, stream, "mvb_effect_hsl_shift_rgba8");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stripe source (movis/layer/texture.py:159-191): a procedural image, pure float64 numpy in the
+// reference.  Every operation below is the IEEE double operation numpy performs, in numpy's order,
+// with no FMA contraction (__dmul_rn / __dadd_rn / __ddiv_rn), so the pixels are bit-identical.
+// ---------------------------------------------------------------------------------------------
+struct StripeParams {
+    uint8_t* dst;
+    int64_t stride;
+    int32_t w, h;
+    int32_t solid;      // 1 / 2: ratio <= 0 / ratio >= 1, the whole image is colour 1 / colour 2
+    int32_t pad_;
+    double v0, v1;      // sin(theta), cos(theta)
+    double cy, cx;      // height / 2, width / 2
+    double width;       // total_width
+    double phase;
+    double edge0, span; // smoothstep: max(ratio - eps, 0), edge1 - edge0
+    double c1[4], c2[4];
+};
+
+__global__ void __launch_bounds__(256)
+k_stripe(const __grid_constant__ StripeParams P)
+{
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= P.w || y >= P.h) return;
+    uint32_t px = 0;
+    if (P.solid) {
+        const double* c = P.solid == 1 ? P.c1 : P.c2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) px |= ((uint32_t)(int)c[k] & 0xFFu) << (8 * k);   // astype(np.uint8)
+    } else {
+        const double iy = __dsub_rn((double)y, P.cy), ix = __dsub_rn((double)x, P.cx);    // np.mgrid - center
+        double p = __dadd_rn(__dmul_rn(P.v0, iy), __dmul_rn(P.v1, ix));                   // (v * inds).sum(axis=0)
+        p = __dadd_rn(__ddiv_rn(p, P.width), P.phase);                                    // / stripe_width + phase
+        p = __dsub_rn(p, floor(p));                                                       // _fract
+        double t = __ddiv_rn(__dsub_rn(p, P.edge0), P.span);                              // _smoothstep
+        t = fmin(fmax(t, 0.0), 1.0);                                                      // np.clip
+        const double sm = __dmul_rn(__dmul_rn(t, t), __dsub_rn(3.0, __dmul_rn(2.0, t)));
+        const double om = __dsub_rn(1.0, sm);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double c = __dadd_rn(__dmul_rn(sm, P.c1[k]), __dmul_rn(om, P.c2[k]));
+            px |= ((uint32_t)(int)c & 0xFFu) << (8 * k);                                  // astype(np.uint8): truncation
+        }
+    }
+    reinterpret_cast<uint32_t*>(P.dst + (int64_t)y * P.stride)[x] = px;
+}
+
+extern "C" int mvb_source_stripe_rgba8(void* dst, int32_t w, int32_t h, int64_t dst_stride, const double params[16],
+                                       int32_t solid, mvb_stream_t stream)
+{
+    if (!dst || !params || w <= 0 || h <= 0 || dst_stride < 4 * (int64_t)w || (dst_stride & 3) ||
+        ((uintptr_t)dst & 3) || solid < 0 || solid > 2)
+        return set_error(MVB_ERR_INVALID_ARG, "bad stripe image / parameters");
+    if (int rc = require_device()) return rc;
+    StripeParams P;
+    std::memset(&P, 0, sizeof P);
+    P.dst = static_cast<uint8_t*>(dst);
+    P.stride = dst_stride;
+    P.w = w;
+    P.h = h;
+    P.solid = solid;
+    P.v0 = params[0]; P.v1 = params[1]; P.cy = params[2]; P.cx = params[3];
+    P.width = params[4]; P.phase = params[5]; P.edge0 = params[6]; P.span = params[7];
+    for (int k = 0; k < 4; k++) { P.c1[k] = params[8 + k]; P.c2[k] = params[12 + k]; }
+    k_stripe<<<dim3((unsigned)((w + 63) / 64), (unsigned)((h + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(P);
+    return check_launch("mvb_source_stripe_rgba8");
+}
+
 extern "C" int mvb_rgb_to_hsv_u8(const uint8_t rgb[3], uint8_t hsv[3])
 {
     if (!rgb || !hsv) return set_error(MVB_ERR_INVALID_ARG, "null argument");

@@ -129,6 +129,53 @@ def s2d_bytes_per_frame(div: int = 1) -> int:
 
 
 # ---------------------------------------------------------------------------------------------
+# Procedural sources: animated Stripe layers under transforms and blend modes
+# ---------------------------------------------------------------------------------------------
+
+def stripe_cases() -> list[dict]:
+    """Constructor arguments of the stand-alone Stripe vectors (tests/golden/stripe.npz)."""
+    rng = np.random.default_rng(77)
+    cases = [
+        dict(size=(100, 100)),                                              # the reference's defaults
+        dict(size=(64, 48), angle=30.0, color1=(10, 200, 30), color2=(250, 20, 90), opacity1=0.7,
+             total_width=17.3, phase=0.2, ratio=0.4),
+        dict(size=(33, 7), angle=90.0, total_width=8.0, ratio=0.0),         # all colour 1
+        dict(size=(5, 9), angle=-12.5, total_width=3.0, ratio=1.0, opacity2=0.25),   # all colour 2
+        dict(size=(1, 1), angle=0.0, total_width=1.0, phase=-0.5),
+        dict(size=(97, 61), angle=0.0, total_width=0.75, phase=1e-3, ratio=0.005),   # edge0 clamps to 0
+        dict(size=(97, 61), angle=180.0, total_width=250.0, phase=-7.25, ratio=0.995),   # edge1 clamps to 1
+    ]
+    for _ in range(9):
+        cases.append(dict(
+            size=(int(rng.integers(2, 160)), int(rng.integers(2, 120))), angle=float(rng.uniform(-400, 400)),
+            color1=tuple(int(v) for v in rng.integers(0, 256, 3)), color2=tuple(int(v) for v in rng.integers(0, 256, 3)),
+            opacity1=float(rng.uniform(0, 1)), opacity2=float(rng.uniform(0, 1)),
+            total_width=float(rng.uniform(0.5, 90)), phase=float(rng.uniform(-3, 3)), ratio=float(rng.uniform(0.02, 0.98))))
+    return cases
+
+
+def build_stripes(mv: Any, div: int = 1, duration: float = 4.0):
+    W, H = 640 // div, 360 // div
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    back = mv.layer.Stripe(size=(W, H), angle=20.0, color1=(20, 40, 90), color2=(200, 220, 240), total_width=48.0 / div)
+    _ramp(back.phase, 0.0, duration, 0.0, 2.0)
+    comp.add_layer(back, name="back")
+    modes = ["normal", "screen", "soft_light", "difference"]
+    for i, mode in enumerate(modes):
+        st = mv.layer.Stripe(size=(200 // div, 160 // div), angle=15.0 + 40.0 * i, color1=(250 - 60 * i, 30 + 50 * i, 80),
+                             color2=(10, 200 - 40 * i, 255 - 30 * i), opacity1=1.0 - 0.2 * i, opacity2=0.35 + 0.15 * i,
+                             total_width=(14.0 + 9.0 * i) / div, ratio=0.3 + 0.1 * i)
+        _ramp(st.angle, 0.0, duration, 15.0 + 40.0 * i, 195.0 - 30.0 * i, "ease_in_out3")
+        _ramp(st.ratio, 0.0, duration, 0.3 + 0.1 * i, 0.9 - 0.15 * i)
+        _ramp(st.color1, 0.0, duration, (250 - 60 * i, 30 + 50 * i, 80), (40, 250, 10 + 60 * i))
+        item = comp.add_layer(st, name=f"s{i}", position=((130 + 125 * i) / div, (120 + 40 * i) / div), blending_mode=mode)
+        _ramp(item.rotation, 0.0, duration, -20.0 * i, 35.0 + 10.0 * i)
+        _ramp(item.scale, 0.0, duration, (1.0, 1.0), (1.3, 0.8))
+        _ramp(item.opacity, 0.0, duration, 1.0, 0.5)
+    return comp
+
+
+# ---------------------------------------------------------------------------------------------
 # S3 (config 2): nested 1080p comp with GaussianBlur / DropShadow / Glow inside a 4K parent
 # ---------------------------------------------------------------------------------------------
 

@@ -33,10 +33,31 @@ def save(name: str, **arrays) -> None:
     print(f"  {name}.npz  {os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3:.0f} kB")
 
 
+def gen_stripe(mv) -> None:
+    """Stripe layers (layer/texture.py:88-191): stand-alone images for scenes.stripe_cases() and frames
+    of scenes.build_stripes (Stripe sources under animated transforms / blend modes)."""
+    out = {}
+    for i, kw in enumerate(scenes.stripe_cases()):
+        out[f"img{i}"] = mv.layer.Stripe(**kw)(0.0)
+    comp = scenes.build_stripes(mv)
+    times = [0.0, 1.37, 3.9]
+    out["times"] = np.asarray(times)
+    for t in times:
+        out[f"frame_{t:.3f}"] = comp(t)
+    comp2 = scenes.build_stripes(mv, div=2)
+    comp2.preview_level = 2 if hasattr(comp2, "preview_level") else 1
+    out["frame_div2_L2"] = comp2(2.2)
+    save("stripe", **out)
+
+
 def main() -> None:
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     mv = import_reference()
+    import sys
+    if "stripe" in sys.argv[1:]:   # only this file (the others are unchanged)
+        gen_stripe(mv)
+        return
     import cv2
     import PIL
     from movis.contrib.segmentation import ChromaKey
@@ -247,6 +268,7 @@ def main() -> None:
     shoot("s2v0d", scenes.build_s2(mv, div=12, variant=0), [round(0.1 + 0.4 * i, 3) for i in range(12)],
           (0, 0, 0, 255), store=False)
     save("scene_frames", **frames)
+    gen_stripe(mv)
     manifest = {
         "reference": "rezoo/movis 0.7.1 (/root/reference, unmodified; Qt/imageio/audio modules stubbed)",
         "numpy": np.__version__, "opencv": cv2.__version__, "pillow": PIL.__version__,

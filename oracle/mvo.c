@@ -712,3 +712,39 @@ MVO_API void mvo_effect_hsl_shift(const uint8_t* src, int w, int h, ptrdiff_t ss
             d[3] = s[3];
         }
 }
+
+/* Stripe.__call__ -- layer/texture.py:159-191.  float64 throughout, one rounding per numpy operation
+ * (this file is compiled with -ffp-contract=off): p = (v0 (y - h/2) + v1 (x - w/2)) / total_width +
+ * phase; p -= floor(p); t = clip((p - edge0) / (edge1 - edge0), 0, 1); s = t t (3 - 2 t);
+ * colour = s c1 + (1 - s) c2, truncated to uint8.  solid = 1 / 2: the early returns of :170-175. */
+MVO_API void mvo_stripe(uint8_t* dst, int w, int h, ptrdiff_t ds, const double v[2], double total_width,
+                        double phase, double edge0, double edge1, const double c1[4], const double c2[4],
+                        int solid)
+{
+    const double cy = (double)h / 2, cx = (double)w / 2;
+    const double span = edge1 - edge0;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            uint8_t* d = dst + (ptrdiff_t)y * ds + 4 * x;
+            if (solid) {
+                for (int k = 0; k < 4; k++) d[k] = (uint8_t)(solid == 1 ? c1[k] : c2[k]);
+                continue;
+            }
+            const double a = v[0] * ((double)y - cy);
+            const double b = v[1] * ((double)x - cx);
+            double p = (a + b) / total_width + phase;
+            p = p - floor(p);
+            double t = (p - edge0) / span;
+            t = t < 0.0 ? 0.0 : t;
+            t = t > 1.0 ? 1.0 : t;
+            const double tt = t * t;
+            const double sm = tt * (3.0 - 2.0 * t);
+            const double om = 1.0 - sm;
+            for (int k = 0; k < 4; k++) {
+                const double u = sm * c1[k];
+                const double q = om * c2[k];
+                d[k] = (uint8_t)(u + q);
+            }
+        }
+}

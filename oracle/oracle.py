@@ -78,6 +78,7 @@ def lib():
         L.mvo_effect_chroma_key.argtypes = [p8, i, i, pd, p8, p8, p8, pd]
         L.mvo_effect_fill_color.argtypes = [p8, i, i, pd, p8, p8, pd]
         L.mvo_effect_hsl_shift.argtypes = [p8, i, i, pd, p8, p8, p8, p8, pd]
+        L.mvo_stripe.argtypes = [p8, i, i, pd, p8, d, d, d, d, p8, p8, i]
         _lib = L
     return _lib
 
@@ -301,6 +302,24 @@ def effect_hsl_shift(img: np.ndarray, hue: float = 0.0, saturation: float = 0.0,
     out = np.empty_like(img)
     lib().mvo_effect_hsl_shift(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(h), _ptr(s), _ptr(v),
                                _ptr(out), out.strides[0])
+    return out
+
+
+def stripe(size: tuple[int, int], angle: float = 45.0, color1=(0, 0, 0), color2=(255, 255, 255),
+           opacity1: float = 1.0, opacity2: float = 1.0, total_width: float = 64.0, phase: float = 0.0,
+           ratio: float = 0.5) -> np.ndarray:
+    """Stripe.__call__ (layer/texture.py:159-191) for already-evaluated attribute values."""
+    width, height = size
+    c1 = np.array([*np.round(np.asarray(color1, dtype=np.float64)), np.round(255 * float(opacity1))], dtype=np.float64)
+    c2 = np.array([*np.round(np.asarray(color2, dtype=np.float64)), np.round(255 * float(opacity2))], dtype=np.float64)
+    ratio = float(ratio)
+    solid = 1 if ratio <= 0.0 else (2 if ratio >= 1.0 else 0)
+    theta = float(angle) / 180.0 * np.pi
+    v = np.array([np.sin(theta), np.cos(theta)], dtype=np.float64)
+    eps = 1e-2
+    out = np.empty((height, width, 4), dtype=np.uint8)
+    lib().mvo_stripe(_ptr(out), width, height, out.strides[0], _ptr(v), float(total_width), float(phase),
+                     max(ratio - eps, 0.0), min(ratio + eps, 1.0), _ptr(c1), _ptr(c2), solid)
     return out
 
 

@@ -65,6 +65,8 @@ def layer_image(item, time: float) -> np.ndarray | None:
         frame = _alpha_matte(layer, layer_time)
     elif _name(layer) == "LuminanceMatte":
         frame = _luminance_matte(layer, layer_time)
+    elif _name(layer) == "Stripe":
+        frame = _stripe(layer, layer_time)
     else:
         frame = layer(layer_time)
     if frame is None:
@@ -72,6 +74,14 @@ def layer_image(item, time: float) -> np.ndarray | None:
     for e in item.effects:
         frame = apply_effect(e, frame, layer_time)
     return frame
+
+
+def _stripe(layer, t):  # layer/texture.py:159-191
+    if t < 0 or t >= layer.duration:
+        return None
+    return O.stripe(tuple(layer.size), float(layer.angle(t)[0]), np.asarray(layer.color1(t)), np.asarray(layer.color2(t)),
+                    float(layer.opacity1(t)[0]), float(layer.opacity2(t)[0]), float(layer.total_width(t)[0]),
+                    float(layer.phase(t)[0]), float(layer.ratio(t)[0]))
 
 
 def _sub(layer, t):

@@ -304,3 +304,25 @@ def test_invalid_arguments_are_rejected(dev):
     assert dev.lib.mvb_composite_stack(t.data_ptr(), 8, 8, 32, bg.ctypes.data, 1, lay.ctypes.data, 0, dev.stream()) == -1
     assert dev.lib.mvb_composite_stack(t.data_ptr(), 8, 8, 30, bg.ctypes.data, 0, None, 0, dev.stream()) == -1
     assert dev.lib.mvb_alpha_composite(t.data_ptr(), 8, 8, 32, t.data_ptr(), 8, 8, 32, 0, 0, 2.0, 0, 0, 0, dev.stream()) == -1
+
+
+def test_stripe_source_golden_and_vs_oracle(dev, golden):
+    """mvb_source_stripe_rgba8 through movis_b200.layer.Stripe: the reference's images, then a seeded sweep
+    (sizes up to 4K, every early-return branch) against the oracle."""
+    import movis_b200 as mv
+    from movis_b200 import scenes
+    from oracle import oracle as O
+    g = golden("stripe")
+    for i, kw in enumerate(scenes.stripe_cases()):
+        assert np.array_equal(mv.layer.Stripe(**kw)(0.0), g[f"img{i}"]), (i, kw)
+    rng = np.random.default_rng(123)
+    sizes = [(3840, 2160), (1921, 1079), (1, 517), (640, 1)] + [(int(rng.integers(1, 700)), int(rng.integers(1, 500))) for _ in range(20)]
+    for size in sizes:
+        kw = dict(angle=float(rng.uniform(-720, 720)), color1=tuple(int(v) for v in rng.integers(0, 256, 3)),
+                  color2=tuple(int(v) for v in rng.integers(0, 256, 3)), opacity1=float(rng.uniform(0, 1)),
+                  opacity2=float(rng.uniform(0, 1)), total_width=float(rng.uniform(0.3, 400)), phase=float(rng.uniform(-5, 5)),
+                  ratio=float(rng.choice([0.0, 1.0, 0.004, 0.996, rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(0, 1)])))
+        got = mv.layer.Stripe(size=size, **kw)(0.0)
+        assert got.shape == (size[1], size[0], 4)
+        assert np.array_equal(got, O.stripe(size, **kw)), (size, kw)
+    assert mv.layer.Stripe(size=(8, 8), duration=1.0)(1.0) is None and mv.layer.Stripe(size=(8, 8))(-0.1) is None

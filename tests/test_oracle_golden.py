@@ -213,3 +213,19 @@ def test_float_bilinear_of_the_stack_kernel_is_exact():
     down = np.floor(exact)                                                 # ulp is 1 in [2^23, 2^24): fma.rm = floor
     assert down.max() < 2 ** 24 and np.array_equal(down.astype(np.float32).astype(np.float64), down)
     assert np.array_equal(down.astype(np.int64) - 12582912, (sums + 512) >> 10)
+
+
+def test_stripe_source_matches_reference(golden):
+    """Stripe (layer/texture.py:88-191): the oracle's float64 restatement against images the reference
+    produced, stand-alone and as animated layers of a composition (oracle scene walker)."""
+    import movis_b200 as mv
+    from movis_b200 import scenes
+    g = golden("stripe")
+    for i, kw in enumerate(scenes.stripe_cases()):
+        kw = dict(kw)
+        assert np.array_equal(O.stripe(kw.pop("size"), **kw), g[f"img{i}"]), (i, kw)
+    comp = scenes.build_stripes(mv)
+    for t in g["times"]:
+        assert np.array_equal(scene_eval.render(comp, float(t), (0, 0, 0, 0)), g[f"frame_{t:.3f}"]), t
+    comp2 = scenes.build_stripes(mv, div=2)
+    assert np.array_equal(scene_eval.render(comp2, 2.2, (0, 0, 0, 0), preview_level=2), g["frame_div2_L2"])
