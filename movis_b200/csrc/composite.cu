@@ -87,7 +87,7 @@ struct TableParams {
 constexpr int kPilOver = 18; // dispatch code of PIL's "over" next to the 18 numpy blend modes
 
 // Host-initialised tables for the division / sqrt heavy blend modes (see BlendTables).
-struct BlendTableData { uint32_t rcp24[260]; uint32_t softg[256]; };
+struct BlendTableData { uint32_t rcp24[260]; float2 softg[256]; };   // softg: see blend_diff2<11> (stack_float.cuh)
 __device__ BlendTableData g_blend_tables;
 
 enum { kTileEdge = 0, kTileEmpty = 1, kTileInterior = 2 };
@@ -230,13 +230,17 @@ static int upload_blend_tables()
     t.rcp24[0] = 0;
     for (int i = 257; i < 260; i++) t.rcp24[i] = 0;
     for (uint32_t b = 0; b < 256; b++) { // g_w3c of imgproc.py:64-68 under uint32 wrap-around
+        uint32_t g;
         if (b < 64) {
             uint32_t v = 16u * b - 780300u * b + 260100u;
             v *= b;
-            t.softg[b] = v / 65025u;
+            g = v / 65025u;
         } else {
-            t.softg[b] = (uint32_t)std::sqrt((double)(255u * b));
+            g = (uint32_t)std::sqrt((double)(255u * b));
         }
+        // the kernel needs D = g - b (uint32) only modulo 255 * 256, split as 255 A + R
+        const uint32_t D = (g - b) % 65280u;
+        t.softg[b] = make_float2((float)(D / 255u), (float)(D % 255u));
     }
     cudaError_t e = cudaMemcpyToSymbol(g_blend_tables, &t, sizeof t);
     if (e != cudaSuccess) return set_error(MVB_ERR_CUDA, cudaGetErrorString(e));

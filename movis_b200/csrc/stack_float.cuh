@@ -32,6 +32,7 @@ typedef unsigned long long u64;
 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: ulp 1, so RN/RM of (magic + x) rounds x to an integer
 constexpr uint32_t kMagicBits = 0x4B400000u;   // float bits of kMagic; bits of (kMagic + k) = kMagicBits + k
 constexpr uint32_t kTwo23Bits = 0x4B000000u;   // float bits of 2^23
+constexpr float kInv65025 = 1.5378702300949953e-05f;   // 0x37810183: the float above 1/65025 (soft_light)
 constexpr float kInv255 = 1.0f / 255.0f;       // 0x3B808081 = 0.00392156886 > 1/255: floor(x * kInv255) == x / 255
                                                // for integers 0 <= x <= 130050 (tests/test_oracle_golden.py)
 constexpr float kNeg255Magic = -3208642560.0f; // -255 * kMagic = -765 * 2^22, exactly representable
@@ -142,7 +143,7 @@ __device__ __forceinline__ u64 ratio255_biased(u64 n, u64 den)
 
 // T(b, f) - b for one colour channel of two rows, biased inputs.
 template <int MODE>
-__device__ __forceinline__ u64 blend_diff2(u64 dB, u64 sB, const uint32_t* softg)
+__device__ __forceinline__ u64 blend_diff2(u64 dB, u64 sB, const float2* softg)
 {
     const u64 kM = bc(kMagic), kM255 = bc(kMagic + 255.0f);
     u64 diff;
@@ -171,14 +172,27 @@ __device__ __forceinline__ u64 blend_diff2(u64 dB, u64 sB, const uint32_t* softg
         diff = min2(sub2(kM255, dB), sub2(sB, kM));
     } else if constexpr (MODE == 9) {                                             // linear_burn: max(-b, f - 255)
         diff = max2(sub2(kM, dB), sub2(sB, kM255));
-    } else if constexpr (MODE == 11) {                                            // soft_light (integer form)
-        float d0, d1, s0, s1;
+    } else if constexpr (MODE == 11) {                                            // soft_light (imgproc.py:58-72)
+        const u64 b = sub2(dB, kM), f = sub2(sB, kM);
+        // f < 128: T - b = -floor((255 - 2f) b (255 - b) / 65025); the numerator stays below 2^22 and
+        // fl_up(1/65025) makes the single fma.rm exact for every (b, f) (tests/test_oracle_golden.py)
+        const u64 kd = fma2(f, bc(-2.0f), bc(255.0f));
+        const u64 qd = fma2_rm(mul2(mul2(b, sub2(kM255, dB)), kd), bc(kInv65025), kM);
+        const u64 dark = sub2(kM, qd);
+        // f >= 128: T = (b + (2f - 255) D[b] // 255) mod 256 with D = g_w3c(b) - b in uint32, as numpy computes
+        // it.  Only T mod 256 survives astype(uint8), and floor(k (D + 65280 m) / 255) = floor(k D / 255)
+        // + 256 k m, so D is reduced mod 65280 and split as 255 A + R: the sum b + k A + floor(k R / 255)
+        // stays exact in fp32.  softg[b] = (A, R).
+        float d0, d1;
         upk(dB, d0, d1);
-        upk(sB, s0, s1);
-        const BlendTables tabs{nullptr, softg};
-        const uint32_t t0 = blend_target_tab<11>(__float_as_uint(d0) & 0xFFu, __float_as_uint(s0) & 0xFFu, tabs);
-        const uint32_t t1 = blend_target_tab<11>(__float_as_uint(d1) & 0xFFu, __float_as_uint(s1) & 0xFFu, tabs);
-        diff = sub2(pk(__uint_as_float(t0 | kMagicBits), __uint_as_float(t1 | kMagicBits)), dB);
+        const float2 ar0 = softg[__float_as_uint(d0) & 0xFFu], ar1 = softg[__float_as_uint(d1) & 0xFFu];
+        const u64 k = fma2(f, bc(2.0f), bc(-255.0f));
+        const u64 q2 = fma2_rm(mul2(k, pk(ar0.y, ar1.y)), bc(kInv255), kM);
+        float t0, t1;
+        upk(add2(fma2(k, pk(ar0.x, ar1.x), q2), b), t0, t1);                      // magic + b + k A + floor(k R / 255)
+        const u64 light = sub2(pk(__uint_as_float((__float_as_uint(t0) & 0xFFu) | kMagicBits),
+                                  __uint_as_float((__float_as_uint(t1) & 0xFFu) | kMagicBits)), dB);
+        diff = select_lt(f, 128.0f, dark, light);
     } else if constexpr (MODE == 12) {                                            // vivid_light (sic)
         const u64 f = sub2(sB, kM), nb = sub2(kM255, dB);
         const u64 d = sub2(add2(nb, kM), ratio255_biased(nb, fma2(f, bc(2.0f), bc(1.0f))));
@@ -204,7 +218,7 @@ __device__ __forceinline__ u64 blend_diff2(u64 dB, u64 sB, const uint32_t* softg
 // Opaque frame (alpha 255 before and after): blend + composite + requantise one colour channel of
 // two rows.  x = fa*T + (255 - fa)*b = fa*(T - b) + 255*b is an integer in [0, 65025].
 template <int MODE>
-__device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const uint32_t* softg)
+__device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const float2* softg)
 {
     const u64 kM = bc(kMagic);
     const u64 x = fma2(fa, blend_diff2<MODE>(dB, sB, softg), fma2(dB, bc(255.0f), bc(kNeg255Magic)));
@@ -234,7 +248,7 @@ struct __align__(16) SlotMem {
 // c1 (T - b) + oa b is below 2^24, so it is exact in fp32; the quotient by the variable oa is
 // q0 = rint(n * rcp(oa)) corrected by the sign of the exact remainder n - q0 oa (|n/oa - q0| < 1).
 template <int MODE>
-__device__ __forceinline__ void over_numpy_rows(RowPairState& d, const u64 (&s)[4], u64 fa, const uint32_t* softg)
+__device__ __forceinline__ void over_numpy_rows(RowPairState& d, const u64 (&s)[4], u64 fa, const float2* softg)
 {
     const u64 kM = bc(kMagic);
     const u64 ba = sub2(d.c[3], kM);
@@ -289,7 +303,7 @@ __device__ __forceinline__ void over_pil_rows(RowPairState& d, const u64 (&s)[4]
 // not a no-op for the numpy arithmetic).
 template <int MODE, bool OPAQUE>
 __device__ __forceinline__ void blend_rows(RowPairState (&d)[2], const u64 (&s)[2][4], const u64 (&fa)[2],
-                                           const uint32_t* softg, unsigned keep)
+                                           const float2* softg, unsigned keep)
 {
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -392,7 +406,7 @@ struct PixelCtx {
 // into the pixels `d`.  `before_tma_wait(info)` runs ahead of the wait on the stage's barrier.
 template <bool OPAQUE, class Slot, class BeforeTmaWait>
 __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, int layer_index, const PixelCtx& C,
-                                           RowPairState (&d)[2], const uint32_t* softg, BeforeTmaWait&& before_tma_wait)
+                                           RowPairState (&d)[2], const float2* softg, BeforeTmaWait&& before_tma_wait)
 {
     const int tx0 = C.tx0, ty0 = C.ty0, x = C.x, rbeg = C.rbeg, lane = C.lane;
     const bool x_ok = C.x_ok;
@@ -541,7 +555,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
     const StackParams& P = PT.s;
     extern __shared__ __align__(1024) uint8_t s_stage[];   // 2 stages of PT.stage_bytes
     __shared__ SlotMem s_slot[kFSlots];         // per resident layer: info, bbox, warp tables, alpha LUT
-    __shared__ uint32_t s_softg[256];
+    __shared__ float2 s_softg[256];
     __shared__ __align__(8) unsigned long long s_bar[8];   // full[0..3], empty[0..3]
     __shared__ int s_class[kMaxLayers];         // per layer: -1 (misses the tile) or kTile* | (partial coverage ? 256 : 0)
     __shared__ int2 s_org[kMaxLayers];          // per layer: TMA box origin in source px

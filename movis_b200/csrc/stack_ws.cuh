@@ -77,7 +77,7 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
     const StackParams& P = PT.s;
     extern __shared__ __align__(1024) uint8_t s_stage[];   // 2 or 4 stages of PT.stage_bytes, then the alpha LUTs
     __shared__ UnitMem s_unit[kWsUnits];
-    __shared__ uint32_t s_softg[256];
+    __shared__ float2 s_softg[256];
     __shared__ int32_t s_cull[kMaxLayers][17];             // first 64 bytes of every DevLayer (17: conflict-free by lane)
     __shared__ __align__(8) unsigned long long s_bar[8 + 2 * kWsUnits];  // full[0..3], empty[0..3], unit_full[], unit_empty[]
 

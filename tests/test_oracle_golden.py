@@ -229,3 +229,30 @@ def test_stripe_source_matches_reference(golden):
         assert np.array_equal(scene_eval.render(comp, float(t), (0, 0, 0, 0)), g[f"frame_{t:.3f}"]), t
     comp2 = scenes.build_stripes(mv, div=2)
     assert np.array_equal(scene_eval.render(comp2, 2.2, (0, 0, 0, 0), preview_level=2), g["frame_div2_L2"])
+
+
+def test_float_soft_light_of_the_stack_kernel_is_exact():
+    """blend_diff2<11> (stack_float.cuh) in float32, emulated with exact float64 products: the dark branch
+    divides by 65025 with one fma.rm against the float above 1/65025; the light branch keeps
+    D = g_w3c(b) - b only modulo 255 * 256, split as 255 A + R, so every intermediate is an exact
+    integer below 2^24.  Checked for every (b, f) against the reference's soft_light table."""
+    c65025 = np.array([0x37810183], dtype=np.uint32).view(np.float32)[0]
+    c255 = np.array([0x3B808081], dtype=np.uint32).view(np.float32)[0]
+    assert np.float32(1.5378702300949953e-05) == c65025 and np.float32(1.0) / np.float32(255.0) == c255
+    x = np.arange(256, dtype=np.uint32)
+    with np.errstate(all="ignore"):   # imgproc.py:64-68, uint32 wrap-around included
+        g = np.where(x < 64, ((16 * x - (12 * 255 ** 2) * x + 4 * (255 ** 2)) * x) // (255 ** 2),
+                     np.sqrt(255 * x).astype(np.int32)).astype(np.uint32)
+    D = ((g - x) % np.uint32(65280)).astype(np.int64)
+    A, R = D // 255, D % 255
+    b = np.arange(256, dtype=np.int64)[:, None]
+    f = np.arange(256, dtype=np.int64)[None, :]
+    N = (255 - 2 * f) * b * (255 - b)
+    assert N[:, :128].max() < 2 ** 22
+    dark = b - np.floor(N.astype(np.float64) * np.float64(c65025)).astype(np.int64)
+    k = 2 * f - 255
+    kR = k * R[:, None]
+    assert kR[:, 128:].max() <= 130050 and (b + k * A[:, None] + kR // 255)[:, 128:].max() < 2 ** 22
+    light = (b + k * A[:, None] + np.floor(kR.astype(np.float64) * np.float64(c255)).astype(np.int64)) % 256
+    T = np.where(f < 128, dark, light)
+    assert np.array_equal(T.astype(np.uint8), O.blend_lut("soft_light"))
