@@ -400,9 +400,9 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
             if (dev != smem_dev) {
                 cudaFuncSetAttribute(k_stack_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxStageBytes);
                 cudaFuncSetAttribute(k_stack_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     4 * kMaxStageBytes + kMaxLayers * 1024);
+                                     5 * kMaxStageBytes + kMaxLayers * 1024);
                 cudaFuncSetAttribute(k_stack_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     4 * kMaxStageBytes + kMaxLayers * 1024);
+                                     5 * kMaxStageBytes + kMaxLayers * 1024);
                 cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
                 smem_dev = dev;
             }
@@ -417,12 +417,32 @@ static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t
             }
             PT.stage_bytes = (stage + 127) & ~127;
             PT.stages_log2 = 4 * PT.stage_bytes <= 36 * 1024 ? 2 : 1;   // keep 3-4 CTAs per SM resident
+            static const int force_stages = [] {   // diagnostics: MVB_STAGES_LOG2=1..3
+                const char* e = std::getenv("MVB_STAGES_LOG2");
+                return e ? std::atoi(e) : 0;
+            }();
+            if (force_stages >= 1 && force_stages <= 3 && ((size_t)PT.stage_bytes << force_stages) <= 5 * (size_t)kMaxStageBytes)
+                PT.stages_log2 = force_stages;
             if (which == "tile" && opaque) {
+                if (PT.stages_log2 > 2) PT.stages_log2 = 2;
                 k_stack_opaque<<<grid, kFWarps * 32, PT.stage_bytes << PT.stages_log2, stream>>>(PT);
             } else {
                 const int n_tiles = (int)(grid.x * grid.y);
-                const int ctas = n_tiles < 3 * n_sm ? n_tiles : 3 * n_sm;
                 const size_t smem = ((size_t)PT.stage_bytes << PT.stages_log2) + (size_t)n * 1024;
+                // persistent CTAs: exactly as many as are resident at once (a CTA that has to wait for a
+                // slot would start its share of the tiles when the others are done)
+                static thread_local size_t occ_smem[2] = {~(size_t)0, ~(size_t)0};
+                static thread_local int occ_dev[2] = {-1, -1}, occ_val[2] = {0, 0};
+                if (occ_smem[opaque] != smem || occ_dev[opaque] != dev) {
+                    int v = 0;
+                    if (opaque) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_stack_ws<true>, kWsThreads, smem);
+                    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_stack_ws<false>, kWsThreads, smem);
+                    occ_smem[opaque] = smem;
+                    occ_dev[opaque] = dev;
+                    occ_val[opaque] = v < 1 ? 1 : v;
+                }
+                const int per_sm = occ_val[opaque];
+                const int ctas = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
                 // cv2's tables for the whole frame, once per launch (scratch owned by the stream: launches on a
                 // stream are ordered, so the next frame's tables cannot overtake this frame's walk)
                 static thread_local TableParams TP;

@@ -379,6 +379,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
     return v;
 }
 
+constexpr int kMaxStages = 8;   // shared-memory stages of TMA boxes in flight (2, 4 or 8 are used)
 enum { kTileTma = 3, kTileTmaPart = 7 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
 
 // cv2's bilinear weights of a sample at (sumx, sumy) (1/1024 px; 5 fractional bits are used):
@@ -456,7 +457,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
         if (cls == kTileTma) fetch(std::false_type{});
         else fetch(std::true_type{});
         __syncwarp();
-        if (lane == 0) mbar_arrive((uint32_t)info.y + 32);         // this warp is done with the stage
+        if (lane == 0) mbar_arrive((uint32_t)info.y + 8 * kMaxStages);   // this warp is done with the stage
     } else if (cls == kTileInterior) {
         const DevLayer& L = P.layers[layer_index];
         const uint8_t* __restrict__ src = L.src;
@@ -556,7 +557,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
     extern __shared__ __align__(1024) uint8_t s_stage[];   // 2 stages of PT.stage_bytes
     __shared__ SlotMem s_slot[kFSlots];         // per resident layer: info, bbox, warp tables, alpha LUT
     __shared__ float2 s_softg[256];
-    __shared__ __align__(8) unsigned long long s_bar[8];   // full[0..3], empty[0..3]
+    __shared__ __align__(8) unsigned long long s_bar[2 * kMaxStages];   // full[], empty[]
     __shared__ int s_class[kMaxLayers];         // per layer: -1 (misses the tile) or kTile* | (partial coverage ? 256 : 0)
     __shared__ int2 s_org[kMaxLayers];          // per layer: TMA box origin in source px
     __shared__ int s_layer[kFSlots];            // per resident layer: layer index | index among the tile's TMA layers << 8
@@ -564,7 +565,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kFTileH;
-    const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[4]);
+    const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[kMaxStages]);
     const uint32_t stage0 = smem_addr(s_stage);
     const int ns_log2 = PT.stages_log2, ns_mask = (1 << ns_log2) - 1;   // 2 or 4 stages
 
@@ -685,7 +686,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
             const int k = (cls & 3) == kTileTma ? __popc(m_tma & ((1u << li) - 1u)) : 0;
             // x: mode (8 bits) | class (3) | phase parity (bit 11) |
             //    refill: thread 0 re-arms the stage of TMA layer k-1 before this layer (bit 12) | row pitch << 16
-            // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]   w: stage address
+            // y: address of the stage's "full" barrier ("empty" is 8 * kMaxStages bytes on)   z: &lut[-kMagicBits]   w: stage address
             const int refill = k >= 1 && k + ns_mask < n_tma;
             s_slot[tid].info = make_int4((L.pil ? kPilOver : L.mode) | ((cls & 7) << 8) |
                                         (((k >> ns_log2) & 1) << 11) | (refill << 12) | ((L.box_w * 4) << 16),

@@ -79,12 +79,12 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
     __shared__ UnitMem s_unit[kWsUnits];
     __shared__ float2 s_softg[256];
     __shared__ int32_t s_cull[kMaxLayers][17];             // first 64 bytes of every DevLayer (17: conflict-free by lane)
-    __shared__ __align__(8) unsigned long long s_bar[8 + 2 * kWsUnits];  // full[0..3], empty[0..3], unit_full[], unit_empty[]
+    __shared__ __align__(8) unsigned long long s_bar[2 * kMaxStages + 2 * kWsUnits];  // full[], empty[], unit_full[], unit_empty[]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[4]);
-    const uint32_t unit_full = smem_addr(&s_bar[8]), unit_empty = smem_addr(&s_bar[8 + kWsUnits]);
+    const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[kMaxStages]);
+    const uint32_t unit_full = smem_addr(&s_bar[2 * kMaxStages]), unit_empty = smem_addr(&s_bar[2 * kMaxStages + kWsUnits]);
     const uint32_t stage0 = smem_addr(s_stage);
     const int ns_log2 = PT.stages_log2, ns_mask = (1 << ns_log2) - 1;
     // opacity-scaled alpha as float, 256 entries per layer: the same for every tile, so built once per CTA
@@ -94,7 +94,7 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, kWsConsumers);
         }
@@ -231,7 +231,7 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
                     const int pitch = C[6] * 4;   // box_w px
                     UnitSlot& S = U.slot[lane];
                     // x: mode (8 bits) | class (3) | phase parity (bit 11) | row pitch << 16
-                    // y: address of the stage's "full" barrier ("empty" is 32 bytes on)   z: &lut[-kMagicBits]
+                    // y: address of the stage's "full" barrier ("empty" is 8 * kMaxStages bytes on)   z: &lut[-kMagicBits]
                     // w: address the stage would have at source pixel (0, 0): stage - origin
                     S.info = make_int4((C[15] ? kPilOver : C[14]) | ((my_c & 7) << 8) |
                                            (((my_g >> ns_log2) & 1) << 11) | (pitch << 16),
