@@ -406,7 +406,7 @@ struct PixelCtx {
 // or through L1 for layers that cannot be staged), cv2's fixed-point bilinear, opacity LUT, blend
 // into the pixels `d`.  `before_tma_wait(info)` runs ahead of the wait on the stage's barrier.
 template <bool OPAQUE, class Slot, class BeforeTmaWait>
-__device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, int layer_index, const PixelCtx& C,
+__device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, const int* layer_index, const PixelCtx& C,
                                            RowPairState (&d)[2], const float2* softg, BeforeTmaWait&& before_tma_wait)
 {
     const int tx0 = C.tx0, ty0 = C.ty0, x = C.x, rbeg = C.rbeg, lane = C.lane;
@@ -421,16 +421,16 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
     uint32_t t[kFRows][4];
     uint32_t wt[kFRows], wb[kFRows];   // cv2's 2 x 2 weights, two 16-bit values each: (w00, w01), (w10, w11)
     unsigned ok = 0xFu;   // bit q: row q of this thread lies inside the layer's bbox and the frame
-    if ((cls & 3) == kTileTma) {
+    auto staged = [&](auto part_tag) {
         before_tma_wait(info);
         const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
         // Tiles the bbox covers only partly run their own copy of the loop (cls == kTileTmaPart): the box
         // spans the covered part alone, so samples outside it read a dummy address (softg) with weight 0, which
         // makes them transparent (alpha 0 -> lut[0] = 0).  Fully covered tiles carry none of that.
-        auto fetch = [&](auto part_tag) {
+        {
             constexpr bool PART = decltype(part_tag)::value;
             if (PART) {
-                const DevLayer& L = P.layers[layer_index];
+                const DevLayer& L = P.layers[*layer_index & 255];
                 const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
                 ok = 0u;
 #pragma unroll
@@ -453,13 +453,16 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
                 t[q][2] = lds_u32(a + down);
                 t[q][3] = lds_u32(a + down + 4);
             }
-        };
-        if (cls == kTileTma) fetch(std::false_type{});
-        else fetch(std::true_type{});
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive((uint32_t)info.y + 8 * kMaxStages);   // this warp is done with the stage
+    };
+    if (cls == kTileTma) {
+        staged(std::false_type{});
+    } else if (cls == kTileTmaPart) {
+        staged(std::true_type{});
     } else if (cls == kTileInterior) {
-        const DevLayer& L = P.layers[layer_index];
+        const DevLayer& L = P.layers[*layer_index & 255];
         const uint8_t* __restrict__ src = L.src;
         const int ss = L.src_stride;
 #pragma unroll
@@ -474,7 +477,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
             tap_weights(sumx, sumy, wt[k], wb[k]);
         }
     } else {
-        const DevLayer& L = P.layers[layer_index];
+        const DevLayer& L = P.layers[*layer_index & 255];
         const uint8_t* __restrict__ src = L.src;
         const int ss = L.src_stride;
         const int sw = L.src_w, sh = L.src_h;
@@ -707,7 +710,7 @@ k_stack_opaque(const __grid_constant__ StackParamsTma PT)
 
 #pragma unroll 1
         for (int slot = 0; slot < n_here; ++slot) {
-            walk_layer<true>(P, s_slot[slot], s_layer[slot] & 255, px, d, s_softg, [&](const int4& info) {
+            walk_layer<true>(P, s_slot[slot], &s_layer[slot], px, d, s_softg, [&](const int4& info) {
                 if (tid == 0 && (info.x & (1 << 12))) {   // the stage of layer k-1 is free once every warp has read it
                     const int k = s_layer[slot] >> 8;
                     mbar_wait(bar_empty + 8 * ((k - 1) & ns_mask), ((k - 1) >> ns_log2) & 1);
