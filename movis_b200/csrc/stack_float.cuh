@@ -457,7 +457,11 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
         __syncwarp();
         if (lane == 0) mbar_arrive((uint32_t)info.y + 8 * kMaxStages);   // this warp is done with the stage
     };
-    if (cls == kTileTma) {
+    // (an opaque copy of the info word keeps the compiler from folding this test into the switch over the
+    // other classes, which it orders with the common case last)
+    uint32_t hot;
+    asm("mov.b32 %0, %1;" : "=r"(hot) : "r"(info.x));
+    if ((hot & 0x700u) == (uint32_t)kTileTma << 8) {
         staged(std::false_type{});
     } else if (cls == kTileTmaPart) {
         staged(std::true_type{});
