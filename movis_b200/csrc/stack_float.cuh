@@ -382,13 +382,15 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 constexpr int kMaxStages = 8;   // shared-memory stages of TMA boxes in flight (2, 4 or 8 are used)
 enum { kTileTma = 3, kTileTmaPart = 7 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
 
-// cv2's bilinear weights of a sample at (sumx, sumy) (1/1024 px; 5 fractional bits are used):
-// wt = (32 - fx)(32 - fy) | fx (32 - fy) << 16,  wb = (32 - fx) fy | fx fy << 16  (imgwarp.cpp: the
-// INTER_LINEAR table of initInterTab2D, whose entries are these exact products).
+// cv2's bilinear weights of a sample at (sumx, sumy) (1/1024 px; 5 fractional bits are used), times 32:
+// wt = 32 (32 - fx)(32 - fy) | 32 fx (32 - fy) << 16,  wb = 32 (32 - fx) fy | 32 fx fy << 16  (imgwarp.cpp:
+// the INTER_LINEAR table of initInterTab2D, whose entries are these exact products).  The factor 32 is
+// what masking fx in place (sumx & 0x3E0 = 32 fx) leaves instead of shifting it down; every half stays
+// below 2^16 and the weighted sums below 2^23, and the final fma divides it out.
 __device__ __forceinline__ void tap_weights(int sumx, int sumy, uint32_t& wt, uint32_t& wb)
 {
-    const uint32_t fx = (uint32_t)(sumx >> 5) & 31u, fy = (uint32_t)(sumy >> 5) & 31u;
-    const uint32_t a = imad(fx, 0xFFFFu, 32u);   // (32 - fx) | fx << 16
+    const uint32_t fy = (uint32_t)(sumy >> 5) & 31u;
+    const uint32_t a = imad((uint32_t)sumx & 0x3E0u, 0xFFFFu, 1024u);   // 32 (32 - fx) | 32 fx << 16
     wb = a * fy;
     wt = (a << 5) - wb;
 }
@@ -504,8 +506,8 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
 
     // ---- cv2's fixed-point bilinear: out = (sum w p + 512) >> 10 -------------------------------
     // IDP.2A multiplies the two 16-bit weights of a tap row with two bytes: with the taps of a row paired
-    // by channel, four of them give one channel's exact sum; started from the bits of 2^23 + 512 the
-    // accumulator IS the float 2^23 + 512 + sum, and one fma.rm takes floor(. / 1024) of a row pair.
+    // by channel, four of them give one channel's exact sum; started from the bits of 2^23 + 32 * 512 the
+    // accumulator IS the float 2^23 + 32 (512 + sum), and one fma.rm takes floor(. / 1024) of a row pair.
     u64 s[2][4], fa[2];
     // &lut[bits - kMagicBits] for the biased alpha `bits`: one LEA (the shift drops the exponent bits)
     const uint32_t lut_base = (uint32_t)info.z;
@@ -517,14 +519,14 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
             const int k = 2 * p + q;
             const uint32_t t_rg = __byte_perm(t[k][0], t[k][1], 0x5140), t_ba = __byte_perm(t[k][0], t[k][1], 0x7362);
             const uint32_t b_rg = __byte_perm(t[k][2], t[k][3], 0x5140), b_ba = __byte_perm(t[k][2], t[k][3], 0x7362);
-            v[q][0] = __uint_as_float(__dp2a_lo(wb[k], b_rg, __dp2a_lo(wt[k], t_rg, kTwo23Bits + 512u)));
-            v[q][1] = __uint_as_float(__dp2a_hi(wb[k], b_rg, __dp2a_hi(wt[k], t_rg, kTwo23Bits + 512u)));
-            v[q][2] = __uint_as_float(__dp2a_lo(wb[k], b_ba, __dp2a_lo(wt[k], t_ba, kTwo23Bits + 512u)));
-            v[q][3] = __uint_as_float(__dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, kTwo23Bits + 512u)));
+            v[q][0] = __uint_as_float(__dp2a_lo(wb[k], b_rg, __dp2a_lo(wt[k], t_rg, kTwo23Bits + 32u * 512u)));
+            v[q][1] = __uint_as_float(__dp2a_hi(wb[k], b_rg, __dp2a_hi(wt[k], t_rg, kTwo23Bits + 32u * 512u)));
+            v[q][2] = __uint_as_float(__dp2a_lo(wb[k], b_ba, __dp2a_lo(wt[k], t_ba, kTwo23Bits + 32u * 512u)));
+            v[q][3] = __uint_as_float(__dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, kTwo23Bits + 32u * 512u)));
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c)   // (2^23 + 512 + sum) / 1024 = 8192 + (sum + 512) / 1024
-            s[p][c] = fma2_rm(pk(v[0][c], v[1][c]), bc(1.0f / 1024.0f), bc(kMagic - 8192.0f));
+        for (int c = 0; c < 4; ++c)   // (2^23 + 32 (512 + sum)) / 32768 = 256 + (sum + 512) / 1024
+            s[p][c] = fma2_rm(pk(v[0][c], v[1][c]), bc(1.0f / 32768.0f), bc(kMagic - 256.0f));
         float a0, a1;
         upk(s[p][3], a0, a1);
         const uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);

@@ -194,22 +194,23 @@ def test_float_division_constants_of_the_stack_kernel():
 
 
 def test_float_bilinear_of_the_stack_kernel_is_exact():
-    """The bilinear step of stack_float.cuh: the 2 x 2 weights are the exact products (32 - fx)(32 - fy)...
-    packed as 16-bit pairs by two integer multiplies without carries between the halves, the IDP.2A sum
-    started at the bits of 2^23 + 512 is the float 2^23 + 512 + sum (< 2^24), and one fma rounded down,
-    X * 2^-10 + (1.5 * 2^23 - 8192), leaves 1.5 * 2^23 + ((sum + 512) >> 10): cv2's result."""
+    """The bilinear step of stack_float.cuh: the 2 x 2 weights are 32 times the exact products
+    (32 - fx)(32 - fy)... (the 32 is what masking fx in place leaves), packed as 16-bit pairs by integer
+    multiplies without carries between the halves; the IDP.2A sum started at the bits of 2^23 + 32 * 512
+    is the float 2^23 + 32 (512 + sum) (< 2^24), and one fma rounded down, X * 2^-15 + (1.5 * 2^23 - 256),
+    leaves 1.5 * 2^23 + ((sum + 512) >> 10): cv2's result."""
     for fx in range(32):
         for fy in range(32):
-            a = (fx * 0xFFFF + 32) & 0xFFFFFFFF
+            a = ((32 * fx) * 0xFFFF + 1024) & 0xFFFFFFFF
             wb = (a * fy) & 0xFFFFFFFF
             wt = ((a << 5) - wb) & 0xFFFFFFFF
-            assert (wt & 0xFFFF, wt >> 16) == ((32 - fx) * (32 - fy), fx * (32 - fy))
-            assert (wb & 0xFFFF, wb >> 16) == ((32 - fx) * fy, fx * fy)
+            assert (wt & 0xFFFF, wt >> 16) == (32 * (32 - fx) * (32 - fy), 32 * fx * (32 - fy))
+            assert (wb & 0xFFFF, wb >> 16) == (32 * (32 - fx) * fy, 32 * fx * fy)
     sums = np.arange(0, 255 * 1024 + 1, dtype=np.int64)                    # every possible weighted sum
-    bits = (np.uint32(0x4B000000 + 512) + sums.astype(np.uint32))
+    bits = (np.uint32(0x4B000000 + 32 * 512) + (32 * sums).astype(np.uint32))
     X = bits.view(np.float32)
-    assert np.array_equal(X.astype(np.int64), (1 << 23) + 512 + sums) and X.max() < 2 ** 24
-    exact = X.astype(np.float64) / 1024.0 + (12582912.0 - 8192.0)          # the fma before its one rounding
+    assert np.array_equal(X.astype(np.int64), (1 << 23) + 32 * (512 + sums)) and X.max() < 2 ** 24
+    exact = X.astype(np.float64) / 32768.0 + (12582912.0 - 256.0)          # the fma before its one rounding
     down = np.floor(exact)                                                 # ulp is 1 in [2^23, 2^24): fma.rm = floor
     assert down.max() < 2 ** 24 and np.array_equal(down.astype(np.float32).astype(np.float64), down)
     assert np.array_equal(down.astype(np.int64) - 12582912, (sums + 512) >> 10)
