@@ -14,9 +14,9 @@
 // multiply-add rounded towards -inf against the constant 1.5*2^23 ("magic"): the quotient lands
 // in the low mantissa bits.  Pixels, samples and quotients are carried as `magic + value`
 // ("biased"); differences of biased numbers are plain differences.
-//   * vertical lerp:  IDP.4A on byte-interleaved taps, accumulator preset to the bits of 2^23,
-//                     so the dot product comes out as a float (2^23 + v) with no conversion;
-//   * horizontal lerp + (S+512)>>10: three FFMA2 and one FADD2 per channel for TWO rows;
+//   * bilinear:  cv2's 2 x 2 weights as 16-bit pairs, IDP.2A (16 x 8 bit dot product) on taps paired by
+//                channel, accumulator preset to the bits of 2^23 + 32*512, so a channel's exact weighted
+//                sum comes out as a float with no conversion; (S+512)>>10 is one FFMA2.RM for TWO rows;
 //   * blend + composite + floor(./255): four FFMA2/FADD2 per channel for TWO rows (NORMAL).
 // The tile's pixels stay in registers for the whole layer walk (thread = 1 column x 4 rows).
 #pragma once

@@ -8,10 +8,11 @@
 // (grid = a few CTAs per SM, tiles taken round-robin) and has a ninth, PRODUCER warp that runs one
 // or two tiles ahead of the eight CONSUMER warps:
 //
-//   producer   cull + classify the layers against the next tile, build cv2's integer tables and the
-//              opacity LUT for up to 8 layers ("unit") into one of two shared-memory unit buffers,
-//              publish the unit (mbarrier), then request the layers' source boxes through TMA into
-//              a ring of stages as they become free;
+//   producer   cull + classify the layers against the next tile; for up to 8 layers ("unit") write the
+//              info words and bulk-copy the tile's slice of cv2's integer tables (built for the whole
+//              frame by k_stack_tables) into one of four shared-memory unit buffers, whose mbarrier
+//              publishes the unit when the copies have landed; request the layers' source boxes
+//              through TMA into a ring of stages as they become free;
 //   consumers  wait for the unit, walk its layers (taps from the TMA stages, float arithmetic,
 //              pixels in registers), release the unit, store the tile after its last unit.
 //
