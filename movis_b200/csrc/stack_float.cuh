@@ -441,19 +441,24 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
                     if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) ok |= 1u << q;
                 }
             }
-            mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
+            // addresses and weights first: they do not need the texels, so they overlap the box's arrival
+            uint32_t a[kFRows], down[kFRows];
 #pragma unroll
             for (int q = 0; q < kFRows; ++q) {
                 const int2 r = rowtab[q];
                 const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
-                uint32_t a = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
+                a[q] = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
                 tap_weights(sumx, sumy, wt[q], wb[q]);
-                uint32_t down = pitch;
-                if (PART && !(ok >> q & 1)) { a = smem_addr(softg); down = 0u; wt[q] = wb[q] = 0u; }
-                t[q][0] = lds_u32(a);
-                t[q][1] = lds_u32(a + 4);
-                t[q][2] = lds_u32(a + down);
-                t[q][3] = lds_u32(a + down + 4);
+                down[q] = pitch;
+                if (PART && !(ok >> q & 1)) { a[q] = smem_addr(softg); down[q] = 0u; wt[q] = wb[q] = 0u; }
+            }
+            mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
+#pragma unroll
+            for (int q = 0; q < kFRows; ++q) {
+                t[q][0] = lds_u32(a[q]);
+                t[q][1] = lds_u32(a[q] + 4);
+                t[q][2] = lds_u32(a[q] + down[q]);
+                t[q][3] = lds_u32(a[q] + down[q] + 4);
             }
         }
         __syncwarp();
