@@ -335,6 +335,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One arrival for the whole (converged) warp: elect.sync waits for all 32 lanes, so every lane has issued
+// its reads of the buffer being released before the elected lane signals (two instructions instead of
+// the __syncwarp + lane test + branch sequence).
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar)
+{
+    asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; @P mbarrier.arrive.shared::cta.b64 _, [%0]; }"
+                 ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -461,8 +469,7 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
                 t[q][3] = lds_u32(a[q] + down[q] + 4);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive((uint32_t)info.y + 8 * kMaxStages);   // this warp is done with the stage
+        mbar_arrive_warp((uint32_t)info.y + 8 * kMaxStages);   // this warp is done with the stage
     };
     // (an opaque copy of the info word keeps the compiler from folding this test into the switch over the
     // other classes, which it orders with the common case last)

@@ -296,8 +296,7 @@ k_stack_ws(const __grid_constant__ StackParamsTma PT)
 #pragma unroll 1
             for (int slot = 0; slot < n_here; ++slot)
                 walk_layer<OPAQUE>(P, U.slot[slot], &U.layer[slot], px, d, s_softg, [](const int4&) {});
-            __syncwarp();
-            if (lane == 0) mbar_arrive(unit_empty + 8 * (u & (kWsUnits - 1)));   // this warp no longer reads the unit
+            mbar_arrive_warp(unit_empty + 8 * (u & (kWsUnits - 1)));   // this warp no longer reads the unit
             if ((hdr.z & 512) && x_ok) {   // last unit of the tile: one coalesced 128-byte store per warp row
 #pragma unroll
                 for (int k = 0; k < kFRows; ++k) {
