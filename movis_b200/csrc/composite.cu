@@ -337,8 +337,14 @@ static void* table_scratch(cudaStream_t stream, size_t bytes)
     static std::unordered_map<uint64_t, Buf> bufs;
     int dev = 0;
     cudaGetDevice(&dev);
-    const uint64_t key = ((uint64_t)(uintptr_t)stream << 6) ^ (uint64_t)dev;
+    const uint64_t key = ((uint64_t)(uintptr_t)stream << 6) | (uint64_t)(dev & 63);
     std::lock_guard<std::mutex> lock(mu);
+    if (bufs.size() > 64 && !bufs.count(key)) {   // streams come and go: drop this device's idle buffers
+        for (auto it = bufs.begin(); it != bufs.end();) {
+            if ((int)(it->first & 63) == dev) { cudaFree(it->second.p); it = bufs.erase(it); }
+            else ++it;
+        }
+    }
     Buf& b = bufs[key];
     if (b.cap < bytes) {
         if (b.p) cudaFree(b.p);   // synchronises: nothing in flight reads the old buffer afterwards

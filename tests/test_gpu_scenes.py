@@ -195,3 +195,26 @@ def test_stripe_layers_in_a_composition_match_reference_golden(golden):
     comp2 = scenes.build_stripes(mv, div=2)
     with comp2.preview(level=2):
         assert np.array_equal(comp2(2.2), g["frame_div2_L2"])
+
+
+def test_frames_rendered_on_several_streams_are_independent():
+    """mvb_composite_stack keeps one coordinate-table scratch buffer per stream: frames enqueued on
+    different streams back to back (no synchronisation in between) must not disturb one another."""
+    import torch
+    import movis_b200 as mv
+    from movis_b200 import scenes
+    from movis_b200.render import render_frames
+    comp = scenes.build_s2(mv, div=4)
+    times = np.linspace(0.1, 4.8, 12)
+    want = render_frames(comp, times, bg_color=(0, 0, 0, 255)).cpu().numpy()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    H, W = comp.frame_shape()
+    outs = [torch.empty((1, H, W, 4), dtype=torch.uint8, device="cuda") for _ in times]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i, t in enumerate(times):
+            with torch.cuda.stream(streams[(i + rep) % 3]):
+                render_frames(comp, times[i:i + 1], bg_color=(0, 0, 0, 255), out=outs[i])
+        torch.cuda.synchronize()
+        for i in range(len(times)):
+            assert np.array_equal(outs[i][0].cpu().numpy(), want[i]), (rep, i)
