@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmovis_b200.so")
+# MOVIS_B200_LIB: an experiment build of the same library (movis_b200/csrc/Makefile: `make variant`)
+LIB_PATH = os.environ.get("MOVIS_B200_LIB") or os.path.join(_HERE, "csrc", "libmovis_b200.so")
 
 MVB_LAYER_PIL_OVER = 1
 MVB_STACK_KEEP_FRAME = 1

@@ -1,19 +1,21 @@
 // composite.cu -- C-ABI entry points and host side of the fused multi-layer warp + blend kernel,
 // plus the stand-alone warp / alpha_composite operators (sm_100a).  C ABI in include/movis_b200.h.
 //
-// mvb_composite_stack replaces, per frame, the reference's per-layer pair cv2.warpAffine ->
-// alpha_composite (movis/layer/composition.py:811-819) and the frame walk around it
-// (composition.py:363-368).  The device code lives in stack_float.cuh (arithmetic, walk_layer, the
-// one-CTA-per-tile form) and stack_ws.cuh (the persistent warp-specialised kernel that is launched);
-// this file turns mvb_layer records into device records, picks the TMA box of every layer, keeps the
-// cache of TMA descriptors and launches.  Frame and sources are uint8 RGBA HWC in HBM; the frame is
-// written exactly once per launch.
+// mvb_composite_frames replaces the frame loop of Composition._write_video (movis/layer/
+// composition.py:405-413): per frame the reference's per-layer pair cv2.warpAffine -> alpha_composite
+// (composition.py:811-819) and the frame walk around it (composition.py:363-368).  The device code
+// lives in stack_float.cuh (arithmetic, walk_layer) and stack_frames.cuh (k_stack_prep and the
+// persistent warp-specialised k_stack_frames); this file turns mvb_layer records into device records,
+// picks the TMA box of every layer, keeps the cache of TMA descriptors, stages a run of frames and
+// launches: one H2D copy + two kernels per run of up to kMaxRunFrames frames.  Frames and sources
+// are uint8 RGBA HWC in HBM; every frame is written exactly once.
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -29,73 +31,46 @@
 namespace mvb {
 
 constexpr int kTileW = 32;
-constexpr int kTileH = 32;
-constexpr int kMaxLayers = 32; // per launch: device records + TMA descriptors travel as kernel parameters (8.6 KB)
+constexpr int kMaxLayers = 32;   // layers of one frame per launch (one per producer lane); longer stacks continue from the stored frame
+constexpr int kMaxMaps = 128;    // distinct TMA descriptors per launch: they travel as kernel parameters (16 KB)
 
-struct DevLayer {
-    // --- first 64 bytes: what the per-tile cull / classification reads (copied to shared memory) ---
-    int32_t bx, by, bw, bh;
-    int32_t src_w, src_h;
-    int32_t box_w, box_h; // TMA box (source px) that covers the footprint of any 32 x 32 tile; 0: no TMA
-    float mf[6];        // m rounded to float, for the cull only
-    int32_t mode;       // MVB_BLEND_*
-    int32_t pil;        // 1: PIL over
-    // --- the rest ---
-    const uint8_t* src;
-    int32_t src_stride;
-    int32_t pil_a;      // int(round(opacity * 255)) for the PIL path (imgproc.py:207)
-    double m[6];        // inverse map: bbox px -> layer px (OpenCV's own inversion, done on host)
-    double opacity;
-};
-static_assert(sizeof(DevLayer) == 136 && offsetof(DevLayer, src) == 64, "descriptor layout");
-
-struct StackParams {
-    uint8_t* frame;
-    int32_t W, H;
-    int32_t stride;
-    uint32_t bg;
-    int32_t n_layers;
-    int32_t keep_frame;
-    int32_t needs_tables; // some layer uses color_dodge / color_burn / soft_light / vivid_light
-    int32_t pad_;
-    DevLayer layers[kMaxLayers];
-};
-
-// Parameters of the opaque-frame kernel: the stack plus one TMA descriptor per layer (a 2-D tiled
-// map over the layer's source image, box = DevLayer::box_w x box_h pixels, out-of-bounds = 0).
-struct StackParamsTma {
-    StackParams s;
-    int32_t stage_bytes;   // bytes of one shared-memory stage (the largest box of this launch)
-    int32_t stages_log2;   // 1 or 2: two or four stages in flight
-    int32_t ux0, uy0, ux1, uy1;   // union of the layers' bboxes, clipped to the frame: tiles outside it are background only
-    // cv2's integer tables of every layer for the whole frame (k_stack_tables): per layer tab_w entries
-    // (adelta, bdelta) by frame column, then tab_h entries (X0, Y0) by frame row; both padded to tiles
-    const int2* tab;
-    int32_t tab_w, tab_h;
-    int32_t pad_[6];
-    alignas(64) CUtensorMap maps[kMaxLayers];
-};
-
-// Parameters of k_stack_tables: what cv::warpAffine's table set-up needs of each layer.
-struct TableLayer { double m[6]; int32_t bx, by; };
-struct TableParams {
-    int2* tab;
-    int32_t tab_w, tab_h, n_layers, pad_;
-    TableLayer l[kMaxLayers];
-};
+enum { kLayerPil = 1,    // PIL's "over" arithmetic (MVB_LAYER_PIL_OVER)
+       kLayerLut = 2 };  // set by k_stack_prep: the opacity table is not floor(a c) for any c; DevLayer::lut holds it
 
 constexpr int kPilOver = 18; // dispatch code of PIL's "over" next to the 18 numpy blend modes
 
-// Host-initialised tables for the division / sqrt heavy blend modes (see BlendTables).
-struct BlendTableData { uint32_t rcp24[260]; float2 softg[256]; };   // softg: see blend_diff2<11> (stack_float.cuh)
-__device__ BlendTableData g_blend_tables;
+struct DevLayer {
+    // --- first 80 bytes: what the producer warp keeps in shared memory per frame (kCullInts) ---
+    int32_t bx, by, bw, bh;
+    int32_t src_w, src_h;
+    int32_t box_w, box_h; // TMA box (source px) that covers the footprint of any tile; 0: no TMA
+    float mf[6];          // m rounded to float, for the cull only
+    int32_t mode;         // dispatch code: MVB_BLEND_* or kPilOver
+    int32_t flags;        // kLayer*
+    float opac_c;         // k_stack_prep: opacity constant c (walk_layer, stack_float.cuh)
+    int32_t pad0_;
+    int32_t map_index;    // FramesParams::maps[] entry of (src, box)
+    int32_t pad1_;
+    // --- the rest ---
+    const uint8_t* src;
+    float* lut;           // 256 floats of this layer in the run's scratch (written only with kLayerLut)
+    int32_t src_stride;
+    int32_t pil_a;        // int(round(opacity * 255)) for the PIL path (imgproc.py:207)
+    double m[6];          // inverse map: bbox px -> layer px (OpenCV's own inversion, done on host)
+    double opacity;
+};
+static_assert(sizeof(DevLayer) == 160 && offsetof(DevLayer, src) == 80 && offsetof(DevLayer, opac_c) == 64 &&
+              offsetof(DevLayer, map_index) == 72, "descriptor layout");
 
-enum { kTileEdge = 0, kTileEmpty = 1, kTileInterior = 2 };
+// soft_light's table (see blend_diff2<11>, stack_float.cuh): 256 pairs (A, R), a compile-time constant.
+__device__ const float g_softg[512] = {
+#include "softg_table.inc"
+};
 
 } // namespace mvb
 
-#include "stack_float.cuh"   // k_stack_opaque: the float-arithmetic instantiation for opaque frames
-#include "stack_ws.cuh"      // k_stack_ws: its persistent, warp-specialised form (default)
+#include "stack_float.cuh"    // arithmetic + walk_layer
+#include "stack_frames.cuh"   // k_stack_prep, k_stack_frames
 
 namespace mvb {
 
@@ -175,10 +150,8 @@ k_alpha_composite(const __grid_constant__ OverParams P)
 
 static int fill_dev_layer(const mvb_layer& in, DevLayer& out)
 {
-    if (in.bbox_w <= 0 || in.bbox_h <= 0) {
-        std::memset(&out, 0, sizeof(out));
-        return 0; // skipped by the kernel's cull (bw <= 0)
-    }
+    std::memset(&out, 0, sizeof(out));
+    if (in.bbox_w <= 0 || in.bbox_h <= 0) return 0; // skipped by the kernel's cull (bw <= 0)
     if (!in.src || in.src_w <= 0 || in.src_h <= 0 || in.src_w >= 32768 || in.src_h >= 32768)
         return set_error(MVB_ERR_INVALID_ARG, "layer source must be non-null and 1..32767 px per side");
     if (in.src_stride < (int64_t)in.src_w * 4 || (in.src_stride & 3) || in.src_stride > 0x7FFFFFFF ||
@@ -194,16 +167,16 @@ static int fill_dev_layer(const mvb_layer& in, DevLayer& out)
     out.src_w = in.src_w;
     out.src_h = in.src_h;
     out.src_stride = (int32_t)in.src_stride;
-    out.mode = in.blend_mode;
+    const bool pil = (in.flags & MVB_LAYER_PIL_OVER) != 0;
+    out.mode = pil ? kPilOver : in.blend_mode;
+    out.flags = pil ? kLayerPil : 0;
     invert_affine_cv(in.M, out.m);
     out.bx = in.bbox_x;
     out.by = in.bbox_y;
     out.bw = in.bbox_w;
     out.bh = in.bbox_h;
     out.opacity = in.opacity;
-    out.pil = (in.flags & MVB_LAYER_PIL_OVER) ? 1 : 0;
     out.pil_a = (int32_t)std::nearbyint(in.opacity * 255.0);
-    out.box_w = out.box_h = 0;
     for (int i = 0; i < 6; i++) out.mf[i] = (float)out.m[i];
     return 0;
 }
@@ -217,35 +190,6 @@ static int check_image(const void* p, int w, int h, int64_t stride, const char* 
         return set_error(MVB_ERR_INVALID_ARG, buf);
     }
     return 0;
-}
-
-static int upload_blend_tables()
-{
-    static thread_local int uploaded_dev = -1;
-    int dev = -1;
-    cudaGetDevice(&dev);
-    if (dev == uploaded_dev) return MVB_OK;
-    static BlendTableData t;
-    for (uint32_t d = 1; d <= 256; d++) t.rcp24[d] = (uint32_t)(((1ull << 24) + d - 1) / d);
-    t.rcp24[0] = 0;
-    for (int i = 257; i < 260; i++) t.rcp24[i] = 0;
-    for (uint32_t b = 0; b < 256; b++) { // g_w3c of imgproc.py:64-68 under uint32 wrap-around
-        uint32_t g;
-        if (b < 64) {
-            uint32_t v = 16u * b - 780300u * b + 260100u;
-            v *= b;
-            g = v / 65025u;
-        } else {
-            g = (uint32_t)std::sqrt((double)(255u * b));
-        }
-        // the kernel needs D = g - b (uint32) only modulo 255 * 256, split as 255 A + R
-        const uint32_t D = (g - b) % 65280u;
-        t.softg[b] = make_float2((float)(D / 255u), (float)(D % 255u));
-    }
-    cudaError_t e = cudaMemcpyToSymbol(g_blend_tables, &t, sizeof t);
-    if (e != cudaSuccess) return set_error(MVB_ERR_CUDA, cudaGetErrorString(e));
-    uploaded_dev = dev;
-    return MVB_OK;
 }
 
 // ---- TMA descriptors for layer sources ----------------------------------------------------------
@@ -268,18 +212,18 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-// The box a 32 x 32 output tile needs from the source: extent of the tile under the inverse map
-// (|m0| + |m1|) * 31 plus the second tap and the 1/32 px quantisation (5 px), plus up to 3 px
-// because the box must start on a 16-byte boundary of the source row; width a multiple of 8 px
-// and height a multiple of 4 so animated scales share a few descriptors.
-static void choose_box(DevLayer& L)
+// The box a 32 x tile_h output tile needs from the source: extent of the tile under the inverse map
+// (|m0| * 31 + |m1| * (tile_h - 1), likewise in y) plus the second tap and the 1/32 px quantisation
+// (5 px), plus up to 3 px because the box must start on a 16-byte boundary of the source row; width
+// a multiple of 8 px and height a multiple of 4 so animated scales share a few descriptors.
+static void choose_box(DevLayer& L, int tile_h)
 {
     L.box_w = L.box_h = 0;
     static const bool disabled = std::getenv("MVB_DISABLE_TMA") != nullptr;   // diagnostics: gather through L1 instead
     if (disabled) return;
     if ((reinterpret_cast<uintptr_t>(L.src) & 15) || (L.src_stride & 15)) return;   // TMA alignment rules
-    const double ex = 31.0 * (std::fabs(L.m[0]) + std::fabs(L.m[1]));
-    const double ey = 31.0 * (std::fabs(L.m[3]) + std::fabs(L.m[4]));
+    const double ex = 31.0 * std::fabs(L.m[0]) + (tile_h - 1.0) * std::fabs(L.m[1]);
+    const double ey = 31.0 * std::fabs(L.m[3]) + (tile_h - 1.0) * std::fabs(L.m[4]);
     if (!(ex < 250.0 && ey < 250.0)) return;
     const int bw = (((int)std::ceil(ex) + 8) + 7) & ~7, bh = (((int)std::ceil(ey) + 5) + 3) & ~3;
     if (bw > 256 || bh > 256 || bw * bh * 4 > kMaxStageBytes) return;
@@ -303,22 +247,21 @@ struct MapKeyHash {
 };
 
 // A descriptor is a pure function of its key, so entries never go stale; the cache is only bounded.
-static bool tensor_map_for(const DevLayer& L, CUtensorMap* out)
+static bool tensor_map_for(const MapKey& key, CUtensorMap* out)
 {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{L.src, L.src_w, L.src_h, L.src_stride, L.box_w, L.box_h};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) { *out = it->second; return true; }
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)L.src_w, (cuuint64_t)L.src_h};
-    const cuuint64_t strides[1] = {(cuuint64_t)L.src_stride};
-    const cuuint32_t box[2] = {(cuuint32_t)L.box_w, (cuuint32_t)L.box_h};
+    const cuuint64_t dims[2] = {(cuuint64_t)key.w, (cuuint64_t)key.h};
+    const cuuint64_t strides[1] = {(cuuint64_t)key.stride};
+    const cuuint32_t box[2] = {(cuuint32_t)key.bw, (cuuint32_t)key.bh};
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
-    if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(L.src), dims, strides, box, estr,
+    if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(key.src), dims, strides, box, estr,
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
@@ -328,191 +271,315 @@ static bool tensor_map_for(const DevLayer& L, CUtensorMap* out)
     return true;
 }
 
-// Device scratch for the tables of one launch, one buffer per (device, stream), grown on demand and kept.
-// (cudaMallocAsync was tried: its pool trims at every synchronisation and re-allocating stalls the stream.)
-static void* table_scratch(cudaStream_t stream, size_t bytes)
+// ---- per (device, stream) state -------------------------------------------------------------------
+// A run's records, opacity tables and coordinate tables live in ONE device buffer per stream, grown on
+// demand and kept: work on a stream is ordered, so the next run's upload cannot overtake this run's
+// kernels.  The host side of the upload is a ring of pinned staging buffers, each guarded by an event
+// recorded after its copy, so the caller can plan several runs ahead of the device.  Contexts are
+// never evicted (a program uses a handful of streams); they are released at process exit.
+constexpr int kRing = 8;
+struct StreamCtx {
+    uint8_t* dev = nullptr;
+    size_t dev_cap = 0;
+    struct HostSlot { uint8_t* p = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool pending = false; } ring[kRing];
+    int next = 0;
+};
+
+static StreamCtx* stream_ctx(cudaStream_t stream)
 {
-    struct Buf { void* p; size_t cap; };
     static std::mutex mu;
-    static std::unordered_map<uint64_t, Buf> bufs;
+    static std::unordered_map<uint64_t, std::unique_ptr<StreamCtx>> all;
     int dev = 0;
     cudaGetDevice(&dev);
-    const uint64_t key = ((uint64_t)(uintptr_t)stream << 6) | (uint64_t)(dev & 63);
+    const uint64_t key = ((uint64_t)(uintptr_t)stream << 6) ^ (uint64_t)(dev & 63);
     std::lock_guard<std::mutex> lock(mu);
-    if (bufs.size() > 64 && !bufs.count(key)) {   // streams come and go: drop this device's idle buffers
-        for (auto it = bufs.begin(); it != bufs.end();) {
-            if ((int)(it->first & 63) == dev) { cudaFree(it->second.p); it = bufs.erase(it); }
-            else ++it;
-        }
-    }
-    Buf& b = bufs[key];
-    if (b.cap < bytes) {
-        if (b.p) cudaFree(b.p);   // synchronises: nothing in flight reads the old buffer afterwards
-        b.p = nullptr;
-        b.cap = 0;
-        const size_t cap = std::max<size_t>(bytes, (size_t)1 << 20);
-        if (cudaMalloc(&b.p, cap) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return nullptr; }
-        b.cap = cap;
-    }
-    return b.p;
+    auto& slot = all[key];
+    if (!slot) slot.reset(new StreamCtx());
+    return slot.get();
 }
 
-static int launch_stack(void* frame, int W, int H, int64_t stride, const uint8_t bg[4], int n_layers,
-                        const mvb_layer* layers, int flags, cudaStream_t stream)
+static int env_int(const char* name, int fallback)
 {
-    static thread_local StackParamsTma PT;   // 7.6 KB: kept off the stack, reused between launches
-    StackParams& P = PT.s;
-    P.frame = static_cast<uint8_t*>(frame);
+    const char* e = std::getenv(name);
+    return e && *e ? std::atoi(e) : fallback;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// One run: frames[0..nF) with layers[beg[f] .. beg[f] + cnt[f]) each (cnt <= kMaxLayers), one
+// H2D copy + k_stack_prep + k_stack_frames.  Returns the number of frames launched through
+// *launched (fewer than nF when the run needs more than kMaxMaps descriptors; at least one).
+static int launch_run(int nF, void* const* frames, const int32_t* beg, const int32_t* cnt, const mvb_layer* layers,
+                      int W, int H, int64_t stride, const uint8_t bg[4], bool keep, bool opaque, cudaStream_t stream,
+                      int* launched)
+{
+    static const int rows = (MVB_UNITS <= 4 && env_int("MVB_ROWS", 4) == 8) ? 8 : 4;   // rows per thread: tile = 32 x (8 * rows)
+    const int tile_h = kWsConsumers * rows;
+    const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + tile_h - 1) / tile_h;
+    const int tab_w = tiles_x * kTileW, tab_h = tiles_y * tile_h;
+    int nL = 0;
+    for (int f = 0; f < nF; f++) nL += cnt[f];
+
+    int max_cnt = 0;
+    for (int f = 0; f < nF; f++) max_cnt = std::max(max_cnt, (int)cnt[f]);
+    const int tile_stride = 1 + max_cnt;   // int2 entries per (frame, tile) list: count + one per layer
+
+    // device layout: [counter | FrameRec x nF | DevLayer x nL | 256 floats x nL | tables x nL | tile lists]; the first three are uploaded
+    const size_t off_frames = 64;   // [0, 64): the run's work counter, zeroed by the upload
+    const size_t off_layers = align_up(off_frames + (size_t)nF * sizeof(FrameRec), 64);
+    const size_t off_luts = align_up(off_layers + (size_t)nL * sizeof(DevLayer), 256);
+    const size_t off_tab = off_luts + (size_t)nL * 256 * sizeof(float);
+    const size_t off_tiles = align_up(off_tab + (size_t)std::max(nL, 1) * (size_t)(tab_w + tab_h) * sizeof(int2), 256);
+    const size_t total = off_tiles + (size_t)nF * (size_t)(tiles_x * tiles_y) * (size_t)tile_stride * sizeof(int2);
+    StreamCtx* C = stream_ctx(stream);
+    if (C->dev_cap < total) {
+        if (C->dev) cudaFree(C->dev);   // synchronises: nothing in flight reads the old buffer afterwards
+        C->dev = nullptr;
+        C->dev_cap = 0;
+        const size_t cap = std::max<size_t>(total + total / 4, (size_t)1 << 20);
+        if (cudaMalloc(&C->dev, cap) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(MVB_ERR_CUDA, "no device memory for the run's records and warp tables");
+        }
+        C->dev_cap = cap;
+    }
+    StreamCtx::HostSlot& S = C->ring[C->next];
+    C->next = (C->next + 1) % kRing;
+    if (!S.done && cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming) != cudaSuccess)
+        return set_error(MVB_ERR_CUDA, "cudaEventCreate failed");
+    if (S.pending) { cudaEventSynchronize(S.done); S.pending = false; }   // its last upload has been consumed
+    if (S.cap < off_luts) {
+        if (S.p) cudaFreeHost(S.p);
+        S.p = nullptr;
+        S.cap = 0;
+        const size_t cap = std::max<size_t>(off_luts + off_luts / 4, (size_t)64 << 10);
+        if (cudaHostAlloc(&S.p, cap, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(MVB_ERR_CUDA, "no pinned host memory for the run's records");
+        }
+        S.cap = cap;
+    }
+    std::memset(S.p, 0, off_frames);
+    FrameRec* h_frames = reinterpret_cast<FrameRec*>(S.p + off_frames);
+    DevLayer* h_layers = reinterpret_cast<DevLayer*>(S.p + off_layers);
+    DevLayer* d_layers = reinterpret_cast<DevLayer*>(C->dev + off_layers);
+    float* d_luts = reinterpret_cast<float*>(C->dev + off_luts);
+    int2* d_tab = reinterpret_cast<int2*>(C->dev + off_tab);
+    int2* d_tiles = reinterpret_cast<int2*>(C->dev + off_tiles);
+
+    static thread_local FramesParams P;   // 16 KB: kept off the stack, reused between launches
+    static thread_local std::unordered_map<MapKey, int, MapKeyHash> run_maps;
+    run_maps.clear();
+    int n_maps = 0, stage = 0, li = 0, done = 0;
+    for (int f = 0; f < nF; f++) {
+        const int maps_before = n_maps, li_before = li, stage_before = stage;
+        FrameRec& F = h_frames[f];
+        std::memset(&F, 0, sizeof F);
+        F.frame = static_cast<uint8_t*>(frames[f]);
+        F.layers = d_layers + li;
+        F.tab = d_tab + (size_t)li * (size_t)(tab_w + tab_h);
+        F.n_layers = cnt[f];
+        F.ux0 = W; F.uy0 = H; F.ux1 = 0; F.uy1 = 0;
+        bool overflow = false;
+        for (int i = 0; i < cnt[f] && !overflow; i++, li++) {
+            DevLayer& L = h_layers[li];
+            if (int rc = fill_dev_layer(layers[beg[f] + i], L)) return rc;
+            if (L.bw <= 0 || L.bh <= 0) continue;
+            L.lut = d_luts + (size_t)li * 256;
+            F.ux0 = std::min(F.ux0, std::max(L.bx, 0));
+            F.uy0 = std::min(F.uy0, std::max(L.by, 0));
+            F.ux1 = std::max(F.ux1, (int32_t)std::min<int64_t>((int64_t)L.bx + L.bw, W));
+            F.uy1 = std::max(F.uy1, (int32_t)std::min<int64_t>((int64_t)L.by + L.bh, H));
+            choose_box(L, tile_h);
+            if (!L.box_w) continue;
+            const MapKey key{L.src, L.src_w, L.src_h, L.src_stride, L.box_w, L.box_h};
+            auto it = run_maps.find(key);
+            if (it != run_maps.end()) {
+                L.map_index = it->second;
+            } else if (n_maps == kMaxMaps) {
+                overflow = true;   // this frame starts the next run
+                break;
+            } else if (tensor_map_for(key, &P.maps[n_maps])) {
+                run_maps.emplace(key, n_maps);
+                L.map_index = n_maps++;
+            } else {
+                L.box_w = L.box_h = 0;   // no descriptor: gather through L1
+            }
+            if (L.box_w) stage = std::max(stage, L.box_w * L.box_h * 4);
+        }
+        if (overflow) {
+            for (auto it = run_maps.begin(); it != run_maps.end();)
+                it = it->second >= maps_before ? run_maps.erase(it) : std::next(it);
+            n_maps = maps_before;
+            li = li_before;
+            stage = stage_before;
+            break;
+        }
+        done = f + 1;
+    }
+    if (done == 0) return set_error(MVB_ERR_UNSUPPORTED, "a single frame needs more TMA descriptors than a launch takes");
+    nF = done;
+    nL = li;
+    *launched = nF;
+
+    const size_t upload = off_layers + (size_t)nL * sizeof(DevLayer);
+    if (cudaMemcpyAsync(C->dev, S.p, upload, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return check_launch("mvb_composite_frames (upload)");
+    cudaEventRecord(S.done, stream);
+    S.pending = true;
+
+    {
+        PrepParams T;
+        T.layers = d_layers;
+        T.tab = d_tab;
+        T.frames = reinterpret_cast<const FrameRec*>(C->dev + off_frames);
+        T.tiles = d_tiles;
+        T.n_layers = nL;
+        T.n_frames = nF;
+        T.tab_w = tab_w;
+        T.tab_h = tab_h;
+        T.tab_blocks = (tab_w + tab_h + 255) / 256 + 1;
+        T.W = W;
+        T.H = H;
+        T.tile_h = tile_h;
+        T.tiles_x = tiles_x;
+        T.n_tiles = tiles_x * tiles_y;
+        T.tile_stride = tile_stride;
+        T.opaque = opaque ? 1 : 0;
+        T.stride = (int32_t)stride;
+        std::memcpy(&T.bg, bg, 4);
+        T.keep_frame = keep ? 1 : 0;
+        const long long blocks = (long long)nL * T.tab_blocks + (long long)nF * ((T.n_tiles + 7) / 8);
+        if (blocks > 0x7FFFFFFFll) return set_error(MVB_ERR_UNSUPPORTED, "run too large");
+        k_stack_prep<<<(unsigned)blocks, 256, 0, stream>>>(T);
+    }
+
+    P.frames = reinterpret_cast<const FrameRec*>(C->dev + off_frames);
+    P.next_item = reinterpret_cast<unsigned long long*>(C->dev);
+    P.n_frames = nF;
     P.W = W;
     P.H = H;
     P.stride = (int32_t)stride;
     std::memcpy(&P.bg, bg, 4);
-    P.pad_ = 0;
-    if (int rc = upload_blend_tables()) return rc;
+    P.keep_frame = keep ? 1 : 0;
+    P.tab_w = tab_w;
+    P.tab_h = tab_h;
+    P.tiles_x = tiles_x;
+    P.n_tiles = tiles_x * tiles_y;
+    P.tile_stride = tile_stride;
+    P.tiles = d_tiles;
+    P.force_units = 0;
+    P.stage_bytes = (stage + 127) & ~127;
+
+    // kernel variant + its launch geometry (cached per device)
+    typedef void (*Kernel)(const FramesParams);
+    const int variant = (opaque ? 1 : 0) | (rows == 8 ? 2 : 0);
+#if MVB_UNITS <= 4
+    static const Kernel kernels[4] = {k_stack_frames<false, 4>, k_stack_frames<true, 4>,
+                                      k_stack_frames<false, 8>, k_stack_frames<true, 8>};
+#else
+    static const Kernel kernels[4] = {k_stack_frames<false, 4>, k_stack_frames<true, 4>,
+                                      k_stack_frames<false, 4>, k_stack_frames<true, 4>};
+#endif
+    struct Geometry { int dev = -1, n_sm = 0, static_smem = 0, dyn_max = 0, occ_smem = -1, occ = 0; };
+    static thread_local Geometry geo[4];
+    Geometry& Gm = geo[variant];
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (Gm.dev != dev) {
+        Gm = Geometry();
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kernels[variant]) != cudaSuccess) return check_launch("mvb_composite_frames");
+        Gm.static_smem = (int)fa.sharedSizeBytes;
+        Gm.dyn_max = 4 * kMaxStageBytes;
+        // static + dynamic shared memory can exceed 48 KB: opt in once
+        cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, Gm.dyn_max);
+        cudaDeviceGetAttribute(&Gm.n_sm, cudaDevAttrMultiProcessorCount, dev);
+        Gm.dev = dev;
+    }
+    // four stages when they leave room for the CTAs per SM the register budget allows (3 with 4 rows, 2 with 8)
+    const int per_cta = (rows == 8 ? 113 : 75) * 1024 - Gm.static_smem - 1024;
+    P.stages_log2 = 4 * P.stage_bytes <= per_cta ? 2 : 1;
+    static const int force_stages = env_int("MVB_STAGES_LOG2", 0);   // diagnostics: 1..3
+    if (force_stages >= 1 && force_stages <= 3 && ((size_t)P.stage_bytes << force_stages) <= (size_t)Gm.dyn_max)
+        P.stages_log2 = force_stages;
+    const int smem = P.stage_bytes << P.stages_log2;
+    if (Gm.occ_smem != smem) {
+        int v = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernels[variant], kWsThreads, (size_t)smem);
+        Gm.occ_smem = smem;
+        Gm.occ = v < 1 ? 1 : v;
+    }
+    // persistent CTAs: exactly as many as are resident at once (a CTA that has to wait for a slot would
+    // start its share of the items when the others are done)
+    const long long n_items = (long long)nF * P.n_tiles;
+    const int ctas = (int)std::min<long long>(n_items, (long long)Gm.occ * Gm.n_sm);
+    // Programmatic dependent launch: the CTAs may start their prologue while k_stack_prep drains; the
+    // producer warps wait for its results (griddepcontrol.wait) before they read the first record.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kWsThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernels[variant], P);
+    return check_launch("mvb_composite_frames");
+}
+
+// Frames [0, n_frames) with layers[offsets[f] .. offsets[f + 1]) each, split into runs.
+static int launch_frames(int n_frames, void* const* frames, int W, int H, int64_t stride, const uint8_t bg[4],
+                         const int32_t* offsets, const mvb_layer* layers, int flags, cudaStream_t stream)
+{
     // An opaque bg_color keeps the frame's alpha at 255 through every layer (both "over" operators
     // map dst alpha 255 to 255), so the division-free kernel instantiation applies.
-    const bool opaque = bg[3] == 255 && !(flags & MVB_STACK_KEEP_FRAME);
-    const dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH);
-    int done = 0;
-    bool first = true;
-    do {
-        const int n = n_layers - done < kMaxLayers ? n_layers - done : kMaxLayers;
-        for (int i = 0; i < n; i++) {
-            int rc = fill_dev_layer(layers[done + i], P.layers[i]);
-            if (rc) return rc;
+    const bool keep = (flags & MVB_STACK_KEEP_FRAME) != 0;
+    const bool opaque = bg[3] == 255 && !keep;
+    static const int max_run = std::max(1, env_int("MVB_RUN_FRAMES", 32));
+    static const size_t max_tab = (size_t)std::max(1, env_int("MVB_RUN_TABLE_MB", 32)) << 20;
+    const int tiles_x = (W + kTileW - 1) / kTileW;
+    const size_t tab_per_layer = ((size_t)tiles_x * kTileW + (size_t)H + 64) * sizeof(int2);
+    static thread_local std::vector<int32_t> beg, cnt;
+    int f = 0;
+    while (f < n_frames) {
+        const int n = offsets[f + 1] - offsets[f];
+        if (n > kMaxLayers) {
+            // a stack longer than one launch takes: passes of kMaxLayers layers, each continuing from the stored frame
+            for (int done = 0; done < n; done += kMaxLayers) {
+                const int32_t b = offsets[f] + done, c = std::min(kMaxLayers, n - done);
+                int launched = 0;
+                if (int rc = launch_run(1, frames + f, &b, &c, layers, W, H, stride, bg, keep || done > 0, opaque, stream, &launched))
+                    return rc;
+            }
+            f += 1;
+            continue;
         }
-        P.n_layers = n;
-        P.keep_frame = (!first || (flags & MVB_STACK_KEEP_FRAME)) ? 1 : 0;
-        P.needs_tables = 0;
-        for (int i = 0; i < n; i++) {
-            const int m = P.layers[i].mode;
-            if (!P.layers[i].pil && (m == 6 || m == 7 || m == 11 || m == 12)) P.needs_tables = 1;
+        beg.clear();
+        cnt.clear();
+        size_t nL = 0;
+        int f1 = f;
+        while (f1 < n_frames && f1 - f < max_run) {
+            const int c = offsets[f1 + 1] - offsets[f1];
+            if (c > kMaxLayers || (f1 > f && (nL + c) * tab_per_layer > max_tab)) break;
+            beg.push_back(offsets[f1]);
+            cnt.push_back(c);
+            nL += c;
+            ++f1;
         }
-        static const std::string which = [] {   // diagnostics: MVB_STACK_KERNEL=tile selects the one-CTA-per-tile form
-            const char* e = std::getenv("MVB_STACK_KERNEL");
-            return std::string(e ? e : "");
-        }();
-        {
-            int stage = 0;
-            for (int i = 0; i < n; i++) {
-                DevLayer& L = P.layers[i];
-                choose_box(L);
-                if (L.box_w && !tensor_map_for(L, &PT.maps[i])) L.box_w = L.box_h = 0;
-                if (L.box_w && L.box_w * L.box_h * 4 > stage) stage = L.box_w * L.box_h * 4;
-            }
-            static thread_local int smem_dev = -1, n_sm = 0;   // static + dynamic shared memory can exceed 48 KB: opt in once
-            int dev = -1;
-            cudaGetDevice(&dev);
-            if (dev != smem_dev) {
-                cudaFuncSetAttribute(k_stack_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxStageBytes);
-                cudaFuncSetAttribute(k_stack_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     5 * kMaxStageBytes + kMaxLayers * 1024);
-                cudaFuncSetAttribute(k_stack_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     5 * kMaxStageBytes + kMaxLayers * 1024);
-                cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-                smem_dev = dev;
-            }
-            PT.ux0 = W; PT.uy0 = H; PT.ux1 = 0; PT.uy1 = 0;
-            for (int i = 0; i < n; i++) {
-                const DevLayer& L = P.layers[i];
-                if (L.bw <= 0 || L.bh <= 0) continue;
-                PT.ux0 = std::min(PT.ux0, std::max(L.bx, 0));
-                PT.uy0 = std::min(PT.uy0, std::max(L.by, 0));
-                PT.ux1 = std::max(PT.ux1, (int32_t)std::min<int64_t>((int64_t)L.bx + L.bw, W));
-                PT.uy1 = std::max(PT.uy1, (int32_t)std::min<int64_t>((int64_t)L.by + L.bh, H));
-            }
-            PT.stage_bytes = (stage + 127) & ~127;
-            PT.stages_log2 = 4 * PT.stage_bytes <= 36 * 1024 ? 2 : 1;   // keep 3-4 CTAs per SM resident
-            static const int force_stages = [] {   // diagnostics: MVB_STAGES_LOG2=1..3
-                const char* e = std::getenv("MVB_STAGES_LOG2");
-                return e ? std::atoi(e) : 0;
-            }();
-            if (force_stages >= 1 && force_stages <= 3 && ((size_t)PT.stage_bytes << force_stages) <= 5 * (size_t)kMaxStageBytes)
-                PT.stages_log2 = force_stages;
-            if (which == "tile" && opaque) {
-                if (PT.stages_log2 > 2) PT.stages_log2 = 2;
-                k_stack_opaque<<<grid, kFWarps * 32, PT.stage_bytes << PT.stages_log2, stream>>>(PT);
-            } else {
-                const int n_tiles = (int)(grid.x * grid.y);
-                const size_t smem = ((size_t)PT.stage_bytes << PT.stages_log2) + (size_t)n * 1024;
-                // persistent CTAs: exactly as many as are resident at once (a CTA that has to wait for a
-                // slot would start its share of the tiles when the others are done)
-                static thread_local size_t occ_smem[2] = {~(size_t)0, ~(size_t)0};
-                static thread_local int occ_dev[2] = {-1, -1}, occ_val[2] = {0, 0};
-                if (occ_smem[opaque] != smem || occ_dev[opaque] != dev) {
-                    int v = 0;
-                    if (opaque) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_stack_ws<true>, kWsThreads, smem);
-                    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_stack_ws<false>, kWsThreads, smem);
-                    occ_smem[opaque] = smem;
-                    occ_dev[opaque] = dev;
-                    occ_val[opaque] = v < 1 ? 1 : v;
-                }
-                const int per_sm = occ_val[opaque];
-                const int ctas = n_tiles < per_sm * n_sm ? n_tiles : per_sm * n_sm;
-                // cv2's tables for the whole frame, once per launch (scratch owned by the stream: launches on a
-                // stream are ordered, so the next frame's tables cannot overtake this frame's walk)
-                static thread_local TableParams TP;
-                TP.tab_w = PT.tab_w = (int32_t)grid.x * kTileW;
-                TP.tab_h = PT.tab_h = (int32_t)grid.y * kFTileH;
-                TP.n_layers = n;
-                for (int i = 0; i < n; i++) {
-                    std::memcpy(TP.l[i].m, P.layers[i].m, sizeof(TP.l[i].m));
-                    TP.l[i].bx = P.layers[i].bx;
-                    TP.l[i].by = P.layers[i].by;
-                }
-                const size_t tab_bytes = (size_t)(n > 0 ? n : 1) * (size_t)(TP.tab_w + TP.tab_h) * sizeof(int2);
-                void* tab = table_scratch(stream, tab_bytes);
-                if (!tab) return set_error(MVB_ERR_CUDA, "no device memory for the warp tables");
-                TP.tab = static_cast<int2*>(tab);
-                PT.tab = TP.tab;
-                if (n > 0) k_stack_tables<<<dim3((unsigned)((TP.tab_w + TP.tab_h + 255) / 256), (unsigned)n), 256, 0, stream>>>(TP);
-                // Programmatic dependent launch: the stack kernel's CTAs may start their prologue (barriers,
-                // opacity LUTs) while the tables kernel drains; its producer warps wait for the tables
-                // (griddepcontrol.wait) before they copy the first one.
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)ctas);
-                cfg.blockDim = dim3(kWsThreads);
-                cfg.dynamicSmemBytes = smem;
-                cfg.stream = stream;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = n > 0 ? 1 : 0;
-                cfg.attrs = attr;
-                cfg.numAttrs = 1;
-                if (opaque) cudaLaunchKernelEx(&cfg, k_stack_ws<true>, PT);
-                else cudaLaunchKernelEx(&cfg, k_stack_ws<false>, PT);
-            }
-        }
-        done += n;
-        first = false;
-    } while (done < n_layers);
-    return check_launch("mvb_composite_stack");
+        int launched = 0;
+        if (int rc = launch_run(f1 - f, frames + f, beg.data(), cnt.data(), layers, W, H, stride, bg, keep, opaque, stream, &launched))
+            return rc;
+        f += launched;
+    }
+    return MVB_OK;
 }
 
 } // namespace mvb
 
 using namespace mvb;
-
-// Two side streams (+ fork / join events) per device for mvb_composite_frames.
-constexpr int kLanes = 2;
-struct FrameLanes { cudaStream_t stream[kLanes]; cudaEvent_t fork, join[kLanes]; };
-
-static FrameLanes* frame_lanes()
-{
-    static thread_local std::vector<std::pair<int, FrameLanes>> per_device;
-    int dev = -1;
-    cudaGetDevice(&dev);
-    for (auto& e : per_device)
-        if (e.first == dev) return &e.second;
-    FrameLanes L;
-    for (int k = 0; k < kLanes; k++) {
-        if (cudaStreamCreateWithFlags(&L.stream[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&L.join[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
-    if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    per_device.emplace_back(dev, L);
-    return &per_device.back().second;
-}
 
 extern "C" int mvb_max_layers_per_launch(void) { return kMaxLayers; }
 
@@ -523,7 +590,9 @@ extern "C" int mvb_composite_stack(void* frame, int32_t W, int32_t H, int64_t st
     if (int rc = check_image(frame, W, H, stride, "frame")) return rc;
     if (!bg_color || n_layers < 0 || (n_layers > 0 && !layers))
         return set_error(MVB_ERR_INVALID_ARG, "bad bg_color / layers");
-    return launch_stack(frame, W, H, stride, bg_color, n_layers, layers, flags, (cudaStream_t)stream);
+    const int32_t offsets[2] = {0, n_layers};
+    void* frames[1] = {frame};
+    return launch_frames(1, frames, W, H, stride, bg_color, offsets, layers, flags, (cudaStream_t)stream);
 }
 
 extern "C" int mvb_composite_frames(int32_t n_frames, void* const* frames, int32_t W, int32_t H, int64_t stride,
@@ -533,34 +602,12 @@ extern "C" int mvb_composite_frames(int32_t n_frames, void* const* frames, int32
     if (int rc = require_device()) return rc;
     if (n_frames < 0 || (n_frames > 0 && (!frames || !layer_offsets)) || !bg_color)
         return set_error(MVB_ERR_INVALID_ARG, "bad frames / layer_offsets / bg_color");
-    // Frames are independent, and the persistent kernel of one frame drains unevenly (the last CTAs
-    // of a launch leave SMs idle, and the next launch on the same stream waits for all of them): the
-    // frames of a run alternate between two side streams forked from `stream` and joined back into
-    // it, so the next frame's CTAs start on SMs as they come free.
-    FrameLanes* lanes = n_frames >= 2 ? frame_lanes() : nullptr;
-    cudaStream_t user = (cudaStream_t)stream;
-    if (lanes) {
-        cudaEventRecord(lanes->fork, user);
-        for (int k = 0; k < kLanes; k++) cudaStreamWaitEvent(lanes->stream[k], lanes->fork, 0);
-    }
-    int rc = MVB_OK;
-    for (int f = 0; f < n_frames && rc == MVB_OK; f++) {
-        rc = check_image(frames[f], W, H, stride, "frame");
-        if (rc) break;
+    for (int f = 0; f < n_frames; f++) {
+        if (int rc = check_image(frames[f], W, H, stride, "frame")) return rc;
         const int n = layer_offsets[f + 1] - layer_offsets[f];
-        if (n < 0 || (n > 0 && !layers)) {
-            rc = set_error(MVB_ERR_INVALID_ARG, "layer_offsets must be non-decreasing");
-            break;
-        }
-        rc = launch_stack(frames[f], W, H, stride, bg_color, n, layers + layer_offsets[f], flags,
-                          lanes ? lanes->stream[f % kLanes] : user);
+        if (n < 0 || (n > 0 && !layers)) return set_error(MVB_ERR_INVALID_ARG, "layer_offsets must be non-decreasing");
     }
-    if (lanes)
-        for (int k = 0; k < kLanes; k++) {   // join, also after an error: `stream` must see whatever was enqueued
-            cudaEventRecord(lanes->join[k], lanes->stream[k]);
-            cudaStreamWaitEvent(user, lanes->join[k], 0);
-        }
-    return rc;
+    return launch_frames(n_frames, frames, W, H, stride, bg_color, layer_offsets, layers, flags, (cudaStream_t)stream);
 }
 
 extern "C" int mvb_warp_affine_rgba8(const void* src, int32_t sw, int32_t sh, int64_t sstride, void* dst,

@@ -226,21 +226,7 @@ __device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const float2* 
     else return fma2_rm(x, bc(kInv255), kM);                                      // numpy: floor(x/255)
 }
 
-constexpr int kFWarps = 8;   // 256 threads: 8 warps x 4 rows = one 32 x 32 tile
-constexpr int kFRows = 4;
-constexpr int kFTileH = kFWarps * kFRows;
-constexpr int kFSlots = 8;   // layers whose per-tile tables are resident in shared memory at a time
-
 struct RowPairState { u64 c[4]; };   // r, g, b, a of rows (2p, 2p+1), biased (a is unused on opaque frames)
-
-// Everything the layer loop reads about one resident layer, contiguous so that one base address
-// serves all of it (offsets become LDS immediates).
-struct __align__(16) SlotMem {
-    int4 info;               // see the table-building code
-    int2 col[kTileW];        // (adelta, bdelta) per tile column
-    int2 row[kFTileH];       // (X0, Y0) per tile row (relative to the box origin for TMA layers)
-    float lut[256];          // opacity-scaled alpha, as float
-};
 
 // ---- frames whose alpha is not known to be 255 ("general") ----------------------------------------
 // numpy _overlay (imgproc.py:156-170), matte NONE, two rows: with c1 = 255 fa, c2 = ba (255 - fa),
@@ -298,15 +284,15 @@ __device__ __forceinline__ void over_pil_rows(RowPairState& d, const u64 (&s)[4]
     d.c[3] = fma2_rm(v, bc(1.0f / 256.0f), kM);
 }
 
-// Blend the samples of four rows into the thread's pixels.  `keep`: bit q set = row q of this thread
-// lies inside the layer's bbox (only consulted on general frames, where a transparent sample is
-// not a no-op for the numpy arithmetic).
-template <int MODE, bool OPAQUE>
-__device__ __forceinline__ void blend_rows(RowPairState (&d)[2], const u64 (&s)[2][4], const u64 (&fa)[2],
+// Blend the samples of 2 * PAIRS rows into the thread's pixels.  `keep`: bit q set = row q of this
+// thread lies inside the layer's bbox (only consulted on general frames, where a transparent sample
+// is not a no-op for the numpy arithmetic).
+template <int MODE, bool OPAQUE, int PAIRS>
+__device__ __forceinline__ void blend_rows(RowPairState (&d)[PAIRS], const u64 (&s)[PAIRS][4], const u64 (&fa)[PAIRS],
                                            const float2* softg, unsigned keep)
 {
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < PAIRS; ++p) {
         if constexpr (OPAQUE) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) d[p].c[c] = blend_chan<MODE>(d[p].c[c], s[p][c], fa[p], softg);
@@ -347,17 +333,43 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Blocks until the phase with the given parity has completed.  A wait that never completes means
-// a broken descriptor: trap instead of hanging the device.
+// Blocks until the phase with the given parity has completed.  The common case is one try_wait and a
+// branch.  mbarrier.try_wait suspends the thread in the barrier unit for a hardware-defined time, so a
+// longer wait is a short loop of probes (two instructions each).  It is bounded by WALL TIME
+// (%globaltimer, looked at every 2^18 probes), not by a spin count: a slow but live run -- under a
+// debugger, a profiler replay or time slicing -- is left alone, and only a wait that has made no
+// progress for 20 s (a broken descriptor, i.e. a bug) traps instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    for (uint32_t spins = 0;; ++spins) {
-        uint32_t done;
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if (spins > (1u << 22)) __trap();
-    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 n;\n"
+        ".reg .u64 t0, t1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MVB_DONE;\n"
+        "mov.u64 t0, %%globaltimer;\n"
+        "MVB_AGAIN:\n"
+        "mov.u32 n, 0;\n"
+        "MVB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MVB_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MVB_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MVB_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MVB_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 q, n, 65536;\n"
+        "@q bra MVB_WAIT;\n"
+        "mov.u64 t1, %%globaltimer;\n"
+        "sub.u64 t1, t1, t0;\n"
+        "setp.gt.u64 q, t1, 20000000000;\n"
+        "@q trap;\n"
+        "bra MVB_AGAIN;\n"
+        "MVB_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
 }
 // One non-blocking probe of the phase with the given parity.
 __device__ __forceinline__ int mbar_test(uint32_t bar, uint32_t parity)
@@ -372,6 +384,12 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const void* map, int 
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+// 1-D bulk copy global -> shared memory, completion signalled on `bar` in bytes (16-byte granular).
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 // a * b + c on the FMA pipe (IMAD), for address arithmetic the compiler would put on the busier ALU pipe
 __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
@@ -388,7 +406,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 }
 
 constexpr int kMaxStages = 8;   // shared-memory stages of TMA boxes in flight (2, 4 or 8 are used)
-enum { kTileTma = 3, kTileTmaPart = 7 };   // next to kTileEdge / kTileEmpty / kTileInterior: taps come from a TMA-staged box
+// How a layer reaches a tile (decided per tile by the producer warp):
+//   kTileEdge      taps gathered through L1 with full bounds / coverage logic (always valid)
+//   kTileInterior  tile fully inside the bbox and every tap inside the source: unchecked L1 gather
+//   kTileTma       taps come from a TMA-staged box, tile fully inside the bbox (the common case)
+//   kTileTmaPart   TMA-staged box, tile partly outside the bbox
+enum { kTileEdge = 0, kTileInterior = 2, kTileTma = 3, kTileTmaPart = 7 };
 
 // cv2's bilinear weights of a sample at (sumx, sumy) (1/1024 px; 5 fractional bits are used), times 32:
 // wt = 32 (32 - fx)(32 - fy) | 32 fx (32 - fy) << 16,  wb = 32 (32 - fx) fy | 32 fx fy << 16  (imgwarp.cpp:
@@ -403,71 +426,84 @@ __device__ __forceinline__ void tap_weights(int sumx, int sumy, uint32_t& wt, ui
     wt = (a << 5) - wb;
 }
 
+// Frame geometry shared by every frame of a launch.
+struct FrameGeom { int W, H, stride; };
+
 // What identifies a thread's pixels inside the tile being walked.
 struct PixelCtx {
     int tx0, ty0;   // tile origin in the frame
     int x;          // the thread's column
-    int rbeg;       // first of its kFRows rows, relative to ty0
+    int rbeg;       // first of its rows, relative to ty0
     int lane;
     bool x_ok;      // x < frame width
 };
 
-// One layer of the walk for one thread: fetch the taps of its four rows (from the TMA-staged box,
-// or through L1 for layers that cannot be staged), cv2's fixed-point bilinear, opacity LUT, blend
-// into the pixels `d`.  `before_tma_wait(info)` runs ahead of the wait on the stage's barrier.
-template <bool OPAQUE, class Slot, class BeforeTmaWait>
-__device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, const int* layer_index, const PixelCtx& C,
-                                           RowPairState (&d)[2], const float2* softg, BeforeTmaWait&& before_tma_wait)
+// One layer of the walk for one thread: fetch the taps of its ROWS = 4 * QUADS rows (from the TMA-staged
+// box, or through L1 for layers that cannot be staged), cv2's fixed-point bilinear, the opacity scale,
+// blend into the pixels `d`.
+//
+// Opacity: the reference scales the sampled alpha a by the layer's opacity as an integer table
+//   numpy path  fa = trunc(float64(a) * opacity)          (imgproc.py:159)
+//   PIL path    fa = a * int(round(255 opacity)) // 255   (imgproc.py:206-208)
+// k_stack_prep finds, per layer, a constant c = m / 2^18 with floor(a c) == table[a] for all 256 a
+// (it exists unless float64 rounding made the table non-monotone in a / fa, which happens for
+// opacities a few ulps below a fraction of small integers).  Then, with the alpha biased as
+// everything else here (magic + a):   fma.rm(magic + a, c, magic - magic c) = magic + floor(a c),
+// exactly: magic c = 48 m and the addend are representable, the product is exact inside the fma.
+// Layers without such a constant carry a 256-float table in global memory and are walked as
+// kTileEdge, where it is consulted (outside the common path).
+template <bool OPAQUE, int QUADS, class Slot>
+__device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* __restrict__ layers, const Slot& S,
+                                           const int* layer_index, const PixelCtx& C,
+                                           RowPairState (&d)[2 * QUADS], const float2* softg)
 {
-    const int tx0 = C.tx0, ty0 = C.ty0, x = C.x, rbeg = C.rbeg, lane = C.lane;
+    constexpr int ROWS = 4 * QUADS, PAIRS = 2 * QUADS;
+    const int ty0 = C.ty0, x = C.x, rbeg = C.rbeg, lane = C.lane;
     const bool x_ok = C.x_ok;
-    (void)tx0;
     const int4 info = S.info;
     const int cls = (info.x >> 8) & 7;
     const int2 col = S.col[lane];
     const int2* __restrict__ rowtab = &S.row[rbeg];
 
-    // ---- taps of the four rows, all requested before the first is used ----------------------
-    uint32_t t[kFRows][4];
-    uint32_t wt[kFRows], wb[kFRows];   // cv2's 2 x 2 weights, two 16-bit values each: (w00, w01), (w10, w11)
-    unsigned ok = 0xFu;   // bit q: row q of this thread lies inside the layer's bbox and the frame
+    // ---- taps of the rows, all requested before the first is used ----------------------------
+    uint32_t t[ROWS][4];
+    uint32_t wt[ROWS], wb[ROWS];   // cv2's 2 x 2 weights, two 16-bit values each: (w00, w01), (w10, w11)
+    unsigned ok = (1u << ROWS) - 1u;   // bit q: row q of this thread lies inside the layer's bbox and the frame
+    float oc = __int_as_float(info.z); // the layer's opacity constant c (see above)
     auto staged = [&](auto part_tag) {
-        before_tma_wait(info);
         const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
         // Tiles the bbox covers only partly run their own copy of the loop (cls == kTileTmaPart): the box
         // spans the covered part alone, so samples outside it read a dummy address (softg) with weight 0, which
-        // makes them transparent (alpha 0 -> lut[0] = 0).  Fully covered tiles carry none of that.
-        {
-            constexpr bool PART = decltype(part_tag)::value;
-            if (PART) {
-                const DevLayer& L = P.layers[*layer_index & 255];
-                const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
-                ok = 0u;
+        // makes them transparent (alpha 0 -> fa = 0).  Fully covered tiles carry none of that.
+        constexpr bool PART = decltype(part_tag)::value;
+        if (PART) {
+            const DevLayer& L = layers[*layer_index];
+            const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
+            ok = 0u;
 #pragma unroll
-                for (int q = 0; q < kFRows; ++q) {
-                    const int yy = ty0 + rbeg + q;
-                    if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) ok |= 1u << q;
-                }
+            for (int q = 0; q < ROWS; ++q) {
+                const int yy = ty0 + rbeg + q;
+                if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < G.H) ok |= 1u << q;
             }
-            // addresses and weights first: they do not need the texels, so they overlap the box's arrival
-            uint32_t a[kFRows], down[kFRows];
+        }
+        // addresses and weights first: they do not need the texels, so they overlap the box's arrival
+        uint32_t a[ROWS], down[ROWS];
 #pragma unroll
-            for (int q = 0; q < kFRows; ++q) {
-                const int2 r = rowtab[q];
-                const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
-                a[q] = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
-                tap_weights(sumx, sumy, wt[q], wb[q]);
-                down[q] = pitch;
-                if (PART && !(ok >> q & 1)) { a[q] = smem_addr(softg); down[q] = 0u; wt[q] = wb[q] = 0u; }
-            }
-            mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
+        for (int q = 0; q < ROWS; ++q) {
+            const int2 r = rowtab[q];
+            const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px, relative to the box origin
+            a[q] = imad((uint32_t)(sumy >> 10), pitch, imad((uint32_t)(sumx >> 10), 4u, stage));
+            tap_weights(sumx, sumy, wt[q], wb[q]);
+            down[q] = pitch;
+            if (PART && !(ok >> q & 1)) { a[q] = smem_addr(softg); down[q] = 0u; wt[q] = wb[q] = 0u; }
+        }
+        mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
 #pragma unroll
-            for (int q = 0; q < kFRows; ++q) {
-                t[q][0] = lds_u32(a[q]);
-                t[q][1] = lds_u32(a[q] + 4);
-                t[q][2] = lds_u32(a[q] + down[q]);
-                t[q][3] = lds_u32(a[q] + down[q] + 4);
-            }
+        for (int q = 0; q < ROWS; ++q) {
+            t[q][0] = lds_u32(a[q]);
+            t[q][1] = lds_u32(a[q] + 4);
+            t[q][2] = lds_u32(a[q] + down[q]);
+            t[q][3] = lds_u32(a[q] + down[q] + 4);
         }
         mbar_arrive_warp((uint32_t)info.y + 8 * kMaxStages);   // this warp is done with the stage
     };
@@ -480,11 +516,11 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
     } else if (cls == kTileTmaPart) {
         staged(std::true_type{});
     } else if (cls == kTileInterior) {
-        const DevLayer& L = P.layers[*layer_index & 255];
+        const DevLayer& L = layers[*layer_index];
         const uint8_t* __restrict__ src = L.src;
         const int ss = L.src_stride;
 #pragma unroll
-        for (int k = 0; k < kFRows; ++k) {
+        for (int k = 0; k < ROWS; ++k) {
             const int2 r = rowtab[k];
             const int sumx = r.x + col.x, sumy = r.y + col.y;      // 1/1024 px (cv2: X0 + adelta)
             const uint8_t* p = src + ((uint32_t)(sumy >> 10) * (uint32_t)ss + (uint32_t)(sumx >> 10) * 4u);
@@ -495,18 +531,18 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
             tap_weights(sumx, sumy, wt[k], wb[k]);
         }
     } else {
-        const DevLayer& L = P.layers[*layer_index & 255];
+        const DevLayer& L = layers[*layer_index];
         const uint8_t* __restrict__ src = L.src;
         const int ss = L.src_stride;
         const int sw = L.src_w, sh = L.src_h;
         const bool col_in = x_ok && (unsigned)(x - L.bx) < (unsigned)L.bw;
 #pragma unroll
-        for (int k = 0; k < kFRows; ++k) {
+        for (int k = 0; k < ROWS; ++k) {
             const int2 r = rowtab[k];
             const int sumx = r.x + col.x, sumy = r.y + col.y;
             const int yy = ty0 + rbeg + k;
             t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0u;
-            if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < P.H) {
+            if (col_in && (unsigned)(yy - L.by) < (unsigned)L.bh && yy < G.H) {
                 const Taps tp = fetch_taps(src, sw, sh, ss, sumx >> 5, sumy >> 5);
                 t[k][0] = tp.p00; t[k][1] = tp.p01; t[k][2] = tp.p10; t[k][3] = tp.p11;
             } else {
@@ -514,17 +550,31 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
             }
             tap_weights(sumx, sumy, wt[k], wb[k]);
         }
+        if (L.flags & kLayerLut) {
+            // Rare: this layer's opacity table is not floor(a c) for any c.  Take the bilinear alpha here,
+            // look the scaled value v up and give all four taps the alpha v: the common code below then
+            // samples exactly v (the weights sum to 1024) and, with c = 1, leaves it as it is.
+            const float* __restrict__ lut = L.lut;
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) {
+                const uint32_t t_ba = __byte_perm(t[k][0], t[k][1], 0x7362), b_ba = __byte_perm(t[k][2], t[k][3], 0x7362);
+                const uint32_t a = __dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, 32u * 512u)) >> 15;
+                const uint32_t v = (uint32_t)__ldg(lut + a) << 24;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[k][j] = (t[k][j] & 0x00FFFFFFu) | v;
+            }
+            oc = 1.0f;
+        }
     }
 
     // ---- cv2's fixed-point bilinear: out = (sum w p + 512) >> 10 -------------------------------
     // IDP.2A multiplies the two 16-bit weights of a tap row with two bytes: with the taps of a row paired
     // by channel, four of them give one channel's exact sum; started from the bits of 2^23 + 32 * 512 the
     // accumulator IS the float 2^23 + 32 (512 + sum), and one fma.rm takes floor(. / 1024) of a row pair.
-    u64 s[2][4], fa[2];
-    // &lut[bits - kMagicBits] for the biased alpha `bits`: one LEA (the shift drops the exponent bits)
-    const uint32_t lut_base = (uint32_t)info.z;
+    u64 s[PAIRS][4], fa[PAIRS];
+    const u64 oc2 = bc(oc), ok2 = bc(fmaf(oc, -kMagic, kMagic));
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < PAIRS; ++p) {
         float v[2][4];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -539,15 +589,13 @@ __device__ __forceinline__ void walk_layer(const StackParams& P, const Slot& S, 
 #pragma unroll
         for (int c = 0; c < 4; ++c)   // (2^23 + 32 (512 + sum)) / 32768 = 256 + (sum + 512) / 1024
             s[p][c] = fma2_rm(pk(v[0][c], v[1][c]), bc(1.0f / 32768.0f), bc(kMagic - 256.0f));
-        float a0, a1;
-        upk(s[p][3], a0, a1);
-        const uint32_t i0 = __float_as_uint(a0), i1 = __float_as_uint(a1);
-        fa[p] = pk(lds_f32(lut_base + (i0 << 2)), lds_f32(lut_base + (i1 << 2)));
+        // opacity-scaled alpha, plain (not biased): floor(a c) for the two rows in one fma.rm + one subtract
+        fa[p] = sub2(fma2_rm(s[p][3], oc2, ok2), bc(kMagic));
     }
 
     // ---- blend, in the code specialised for this layer's mode ------------------------------------
     switch (info.x & 255) {
-#define MVB_ROWS(M) case M: blend_rows<M, OPAQUE>(d, s, fa, softg, ok); break;
+#define MVB_ROWS(M) case M: blend_rows<M, OPAQUE, PAIRS>(d, s, fa, softg, ok); break;
         MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
         MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)
         MVB_ROWS(15) MVB_ROWS(16) MVB_ROWS(17) MVB_ROWS(18)
@@ -561,198 +609,6 @@ __device__ __forceinline__ int nth_set_bit(unsigned mask, int n)
 {
     for (int q = 0; q < n; ++q) mask &= mask - 1;
     return __ffs((int)mask) - 1;
-}
-
-// One CTA per 32 x 32 output tile, 256 threads, thread = 1 column x 4 rows, pixels in registers.
-//
-// Source texels reach the SM through TMA: for every layer that touches the tile, one elected
-// thread requests the box of the source image that covers the tile's footprint (DevLayer::box_w
-// x box_h px at the tile's own origin, zero-filled outside the image = cv2's BORDER_CONSTANT)
-// into one of two shared-memory stages, one layer ahead of the arithmetic; the 4 taps of a
-// sample are then 4 LDS at tile-local offsets with no bounds logic.  Layers whose source is not
-// 16-byte aligned / too strongly minified for a stage gather through L1 instead (LDG).
-__global__ void __launch_bounds__(kFWarps * 32, 4)
-k_stack_opaque(const __grid_constant__ StackParamsTma PT)
-{
-    const StackParams& P = PT.s;
-    extern __shared__ __align__(1024) uint8_t s_stage[];   // 2 stages of PT.stage_bytes
-    __shared__ SlotMem s_slot[kFSlots];         // per resident layer: info, bbox, warp tables, alpha LUT
-    __shared__ float2 s_softg[256];
-    __shared__ __align__(8) unsigned long long s_bar[2 * kMaxStages];   // full[], empty[]
-    __shared__ int s_class[kMaxLayers];         // per layer: -1 (misses the tile) or kTile* | (partial coverage ? 256 : 0)
-    __shared__ int2 s_org[kMaxLayers];          // per layer: TMA box origin in source px
-    __shared__ int s_layer[kFSlots];            // per resident layer: layer index | index among the tile's TMA layers << 8
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kFTileH;
-    const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[kMaxStages]);
-    const uint32_t stage0 = smem_addr(s_stage);
-    const int ns_log2 = PT.stages_log2, ns_mask = (1 << ns_log2) - 1;   // 2 or 4 stages
-
-    // ---- cull + classify the layers against this tile ---------------------------------------------
-    // Warp 0 classifies one layer per lane; the others meanwhile set up their pixels.
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, kFWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    s_softg[tid] = g_blend_tables.softg[tid];   // unconditional: a predicated LDG makes ptxas re-derive the
-                                                // global-memory descriptor (R2UR) in front of every load
-    if (warp == 0) {
-        int cls = -1;   // -1: the layer does not touch this tile
-        int2 org = make_int2(0, 0);
-        if (lane < P.n_layers) {
-            const DevLayer& L = P.layers[lane];
-            const int bx = L.bx, by = L.by, bw = L.bw, bh = L.bh, src_w = L.src_w, src_h = L.src_h;
-            const int box_w = L.box_w, box_h = L.box_h;
-            const float m0 = L.mf[0], m1 = L.mf[1], m2 = L.mf[2], m3 = L.mf[3], m4 = L.mf[4], m5 = L.mf[5];
-            // tile ∩ bbox ∩ frame, in bbox coordinates (inclusive corners)
-            const int u0 = max(tx0, bx) - bx, u1 = min(min(tx0 + kTileW, bx + bw), P.W) - 1 - bx;
-            const int v0 = max(ty0, by) - by, v1 = min(min(ty0 + kFTileH, by + bh), P.H) - 1 - by;
-            if (bw > 0 && bh > 0 && u0 <= u1 && v0 <= v1) {
-                // source-space extent of that rectangle (affine: centre +- sum |coef| * half size); 0.25 px
-                // of slack covers the 1/32 px coordinate quantisation and its +16/1024 rounding offset
-                // (fp32: positions below 32768 px are good to 0.01 px, far inside that slack)
-                const float uc = 0.5f * (float)(u0 + u1), vc = 0.5f * (float)(v0 + v1);
-                const float hu = 0.5f * (float)(u1 - u0), hv = 0.5f * (float)(v1 - v0);
-                const float xc = m0 * uc + m1 * vc + m2, ex = fabsf(m0) * hu + fabsf(m1) * hv;
-                const float yc = m3 * uc + m4 * vc + m5, ey = fabsf(m3) * hu + fabsf(m4) * hv;
-                const float xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
-                const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == kFTileH - 1;
-                // (no tap inside the source: a no-op on an opaque frame -> stays -1)
-                if (!(xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f)) {
-                    cls = kTileEdge;
-                    // taps span [floor(xmin) - 1, floor(xmax) + 2] at most (same slack as above); TMA wants
-                    // the box to start on a 16-byte boundary of the row: x origin a multiple of 4 px
-                    const int fx0 = ((int)floorf(xmin) - 1) & ~3, fy0 = (int)floorf(ymin) - 1;
-                    if (box_w > 0 && (int)floorf(xmax) + 3 - fx0 <= box_w && (int)floorf(ymax) + 3 - fy0 <= box_h) {
-                        cls = full ? kTileTma : kTileTmaPart;
-                        org = make_int2(fx0, fy0);
-                    } else if (full && xmin > 0.25f && xmax < src_w - 1.25f && ymin > 0.25f && ymax < src_h - 1.25f) {
-                        cls = kTileInterior;   // whole tile covered and every tap inside the source
-                    }
-                }
-            }
-        }
-        s_class[lane] = cls;
-        s_org[lane] = org;
-    }
-
-    // ---- the thread's pixels: column `lane`, rows [4 warp, 4 warp + 4), in registers --------------
-    const int x = tx0 + lane;
-    const int rbeg = warp * kFRows;
-    const bool x_ok = x < P.W;
-    const PixelCtx px{tx0, ty0, x, rbeg, lane, x_ok};
-    RowPairState d[2];
-    if (P.keep_frame) {   // continuing a stack of more than kMaxLayers layers: alpha is 255 already
-        uint32_t v[kFRows];
-#pragma unroll
-        for (int k = 0; k < kFRows; ++k)   // clamped, not predicated (see s_softg above); out-of-frame threads never store
-            v[k] = reinterpret_cast<const uint32_t*>(P.frame + (int64_t)min(ty0 + rbeg + k, P.H - 1) * P.stride)[min(x, P.W - 1)];
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                d[p].c[c] = pk(__uint_as_float(__byte_perm(v[2 * p], kMagicBits, 0x7650 + c)),
-                               __uint_as_float(__byte_perm(v[2 * p + 1], kMagicBits, 0x7650 + c)));
-    } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) d[0].c[c] = d[1].c[c] = bc(kMagic + (float)((P.bg >> (8 * c)) & 0xFFu));
-    }
-    __syncthreads();
-    // every warp derives the paint-ordered list of active layers from the class table by itself
-    const int my_cls = s_class[lane];
-    const unsigned m_act = __ballot_sync(0xFFFFFFFFu, my_cls >= 0);
-    const unsigned m_tma = __ballot_sync(0xFFFFFFFFu, my_cls >= 0 && (my_cls & 3) == kTileTma);
-    const int n_active = __popc(m_act);
-    const int n_tma = __popc(m_tma);
-
-    // Request the box of the k-th TMA layer of this tile into stage k mod n_stages (thread 0 only).
-    auto request = [&](int k) {
-        const int li = nth_set_bit(m_tma, k);
-        const DevLayer& L = P.layers[li];
-        const int2 org = s_org[li];
-        const uint32_t bar = bar_full + 8 * (k & ns_mask);
-        mbar_arrive_expect_tx(bar, (uint32_t)(L.box_w * L.box_h * 4));
-        tma_load_box(stage0 + (k & ns_mask) * PT.stage_bytes, &PT.maps[li], org.x, org.y, bar);
-    };
-    if (tid == 0)
-        for (int k = 0; k < min(n_tma, ns_mask + 1); ++k) request(k);
-
-    unsigned m_rest = m_act;   // active layers not yet walked, in paint order
-    for (int base = 0; base < n_active; base += kFSlots) {
-        const int n_here = min(kFSlots, n_active - base);
-        if (base > 0) __syncthreads();
-        for (int i = tid; i < n_here * (kTileW + kFTileH); i += kFWarps * 32) {
-            const int slot = i / (kTileW + kFTileH), j = i % (kTileW + kFTileH);
-            const int li = nth_set_bit(m_rest, slot);
-            const DevLayer& L = P.layers[li];
-            if (j < kTileW) {
-                const int u = tx0 + j - L.bx;
-                s_slot[slot].col[j] = make_int2(warp_adelta(L.m, u), warp_bdelta(L.m, u));
-            } else {
-                const int v = ty0 + (j - kTileW) - L.by;
-                const int2 org = s_org[li];   // (0, 0) unless the layer is staged by TMA
-                s_slot[slot].row[j - kTileW] = make_int2(warp_x0(L.m, v) - org.x * 1024, warp_y0(L.m, v) - org.y * 1024);
-            }
-        }
-        if (tid < n_here) {   // what the layer loop needs, one 16-byte read per layer
-            const int li = nth_set_bit(m_rest, tid);
-            const DevLayer& L = P.layers[li];
-            const int cls = s_class[li];
-            const int k = (cls & 3) == kTileTma ? __popc(m_tma & ((1u << li) - 1u)) : 0;
-            // x: mode (8 bits) | class (3) | phase parity (bit 11) |
-            //    refill: thread 0 re-arms the stage of TMA layer k-1 before this layer (bit 12) | row pitch << 16
-            // y: address of the stage's "full" barrier ("empty" is 8 * kMaxStages bytes on)   z: &lut[-kMagicBits]   w: stage address
-            const int refill = k >= 1 && k + ns_mask < n_tma;
-            s_slot[tid].info = make_int4((L.pil ? kPilOver : L.mode) | ((cls & 7) << 8) |
-                                        (((k >> ns_log2) & 1) << 11) | (refill << 12) | ((L.box_w * 4) << 16),
-                                    (int)(bar_full + 8 * (k & ns_mask)),
-                                    (int)(smem_addr(s_slot[tid].lut) - (kMagicBits << 2)),
-                                    (int)(stage0 + (k & ns_mask) * PT.stage_bytes));
-            s_layer[tid] = li | (k << 8);
-        }
-        for (int slot = 0; slot < n_here; ++slot, m_rest &= m_rest - 1) {   // 256 threads: one LUT entry each
-            const DevLayer& L = P.layers[__ffs((int)m_rest) - 1];
-            uint32_t v = (uint32_t)tid;
-            if (L.opacity < 1.0)
-                v = L.pil ? (uint32_t)(tid * L.pil_a) / 255u                        // imgproc.py:206-208
-                          : __double2uint_rz(__dmul_rn((double)tid, L.opacity));    // imgproc.py:159
-            s_slot[slot].lut[tid] = (float)v;
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int slot = 0; slot < n_here; ++slot) {
-            walk_layer<true>(P, s_slot[slot], &s_layer[slot], px, d, s_softg, [&](const int4& info) {
-                if (tid == 0 && (info.x & (1 << 12))) {   // the stage of layer k-1 is free once every warp has read it
-                    const int k = s_layer[slot] >> 8;
-                    mbar_wait(bar_empty + 8 * ((k - 1) & ns_mask), ((k - 1) >> ns_log2) & 1);
-                    request(k + ns_mask);
-                }
-            });
-        }
-    }
-
-    // ---- epilogue: one coalesced 128-byte store per warp row ---------------------------------------
-    if (x_ok) {
-#pragma unroll
-        for (int k = 0; k < kFRows; ++k) {
-            if (ty0 + rbeg + k >= P.H) break;
-            float r0, r1, g0, g1, b0, b1;
-            upk(d[k >> 1].c[0], r0, r1);
-            upk(d[k >> 1].c[1], g0, g1);
-            upk(d[k >> 1].c[2], b0, b1);
-            const uint32_t rb = __float_as_uint((k & 1) ? r1 : r0), gb = __float_as_uint((k & 1) ? g1 : g0);
-            const uint32_t bb = __float_as_uint((k & 1) ? b1 : b0);
-            const uint32_t px = __byte_perm(__byte_perm(rb, gb, 0x0040), bb, 0x0410) | 0xFF000000u;
-            reinterpret_cast<uint32_t*>(P.frame + (int64_t)(ty0 + rbeg + k) * P.stride)[x] = px;
-        }
-    }
 }
 
 } // namespace mvb

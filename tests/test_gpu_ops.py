@@ -326,3 +326,92 @@ def test_stripe_source_golden_and_vs_oracle(dev, golden):
         assert got.shape == (size[1], size[0], 4)
         assert np.array_equal(got, O.stripe(size, **kw)), (size, kw)
     assert mv.layer.Stripe(size=(8, 8), duration=1.0)(1.0) is None and mv.layer.Stripe(size=(8, 8))(-0.1) is None
+
+
+# opacities whose float64 table trunc(a * opacity) is NOT floor(a * c) for any c (a few ulps below a
+# fraction of small integers): k_stack_prep must detect them and fall back to the stored table
+AWKWARD_OPACITIES = [0.19999999999999998, 0.39999999999999997, 0.7999999999999999, 0.8333333333333333,
+                     0.09999999999999999, 0.988235294117647]
+
+
+def test_stack_opacity_constant_and_table_fallback_vs_oracle(dev):
+    """The fused kernel scales the sampled alpha by one fma per row pair (constant found per layer by
+    k_stack_prep) instead of the reference's 256-entry table; every alpha value x many opacities, both
+    arithmetic paths, opaque and translucent frames, incl. the opacities that need the table."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    n = 256
+    fg = rng.integers(0, 256, (n, n, 4), dtype=np.uint8)
+    fg[..., 3] = np.arange(n, dtype=np.uint8)[None, :]
+    base = rng.integers(0, 256, (n, n, 4), dtype=np.uint8)
+    ops = AWKWARD_OPACITIES + [0.0, 1.0, 0.5, 1 / 255, 254 / 255, 0.2, 0.7, 1 / 3, 2 / 3, 0.999999, 1e-9]
+    ops += [float(v) for v in rng.random(12)]
+    for frame_alpha in (255, None):
+        bgimg = base.copy()
+        if frame_alpha is not None:
+            bgimg[..., 3] = frame_alpha
+        for mode, pil in ((0, True), (1, False), (11, False)):
+            for op in ops:
+                if frame_alpha is None:
+                    got = _stack(dev, n, n, (0, 0, 0, 0), [(fg, (0, 0), mode, pil, op)], flags=1, initial=bgimg)
+                else:
+                    got = _stack(dev, n, n, (1, 2, 3, 255), [(bgimg, (0, 0), 0, True, 1.0), (fg, (0, 0), mode, pil, op)])
+                want = O.alpha_composite(bgimg.copy(), fg, (0, 0), op, mode, 0, use_pil=pil)
+                assert np.array_equal(got, want), (frame_alpha, mode, pil, op)
+
+
+def _frames_call(dev, W, H, bg_color, per_frame_layers):
+    """mvb_composite_frames over identity-warp layers: per frame a list of (tensor, (x, y), mode, pil, opacity)."""
+    import torch
+    n = len(per_frame_layers)
+    offsets = np.zeros(n + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum([len(l) for l in per_frame_layers])
+    rows = np.zeros(int(offsets[-1]), dtype=dev.native.LAYER_DTYPE)
+    k = 0
+    for layers in per_frame_layers:
+        for (t, pos, mode, pil, op) in layers:
+            p, w, h, s = dev.args(t)
+            rows[k]["src"], rows[k]["src_w"], rows[k]["src_h"], rows[k]["src_stride"] = p, w, h, s
+            rows[k]["M"] = [1, 0, 0, 0, 1, 0]
+            rows[k]["bbox_x"], rows[k]["bbox_y"], rows[k]["bbox_w"], rows[k]["bbox_h"] = pos[0], pos[1], w, h
+            rows[k]["blend_mode"], rows[k]["flags"], rows[k]["opacity"] = mode, 1 if pil else 0, op
+            k += 1
+    out = torch.empty((n, H, W, 4), dtype=torch.uint8, device="cuda")
+    ptrs = (out.data_ptr() + out.stride(0) * np.arange(n, dtype=np.int64)).astype(np.uint64)
+    bg = np.asarray(bg_color, dtype=np.uint8)
+    dev.native.check(dev.lib.mvb_composite_frames(n, ptrs.ctypes.data, W, H, out.stride(1), bg.ctypes.data,
+                                                  offsets.ctypes.data, rows.ctypes.data if len(rows) else None, 0, dev.stream()))
+    return dev.down(out)
+
+
+def test_frames_call_splits_runs_by_descriptors_and_long_stacks(dev):
+    """One mvb_composite_frames call whose frames need more distinct TMA descriptors than a launch
+    carries (every layer has its own source image), with empty frames and a 40-layer frame in the
+    middle: every frame must equal the same stack rendered alone through mvb_composite_stack."""
+    import torch
+    rng = np.random.default_rng(9)
+    W, H = 96, 80
+    pool = torch.from_numpy(rng.integers(0, 256, (260, 48, 64, 4), dtype=np.uint8)).cuda()
+    per_frame, k = [], 0
+    for f in range(44):
+        n_layers = 40 if f == 20 else (0 if f in (3, 43) else 5)
+        layers = []
+        for i in range(n_layers):
+            pos = (int(rng.integers(-20, W - 10)), int(rng.integers(-20, H - 10)))
+            mode = int(rng.integers(0, 18))
+            layers.append((pool[k % 260], pos, mode, mode == 0, float(rng.choice([1.0, 0.6, 0.25]))))
+            k += 1
+        per_frame.append(layers)
+    for bg in ((5, 6, 7, 255), (0, 0, 0, 0)):
+        got = _frames_call(dev, W, H, bg, per_frame)
+        for f, layers in enumerate(per_frame):
+            want = _frames_call(dev, W, H, bg, [layers])[0]
+            assert np.array_equal(got[f], want), (bg, f)
+        # and the single-frame path against the oracle for a few of them
+        from oracle import oracle as O
+        for f in (0, 20, 43):
+            ref = np.empty((H, W, 4), np.uint8)
+            ref[...] = np.asarray(bg, np.uint8)
+            for (t, pos, mode, pil, op) in per_frame[f]:
+                ref = O.alpha_composite(ref, t.cpu().numpy(), pos, op, mode, 0, use_pil=pil)
+            assert np.array_equal(got[f], ref), (bg, f)
