@@ -35,7 +35,6 @@ constexpr uint32_t kTwo23Bits = 0x4B000000u;   // float bits of 2^23
 constexpr float kInv65025 = 1.5378702300949953e-05f;   // 0x37810183: the float above 1/65025 (soft_light)
 constexpr float kInv255 = 1.0f / 255.0f;       // 0x3B808081 = 0.00392156886 > 1/255: floor(x * kInv255) == x / 255
                                                // for integers 0 <= x <= 130050 (tests/test_oracle_golden.py)
-constexpr float kNeg255Magic = -3208642560.0f; // -255 * kMagic = -765 * 2^22, exactly representable
 
 __device__ __forceinline__ u64 pk(float lo, float hi)
 {
@@ -216,14 +215,16 @@ __device__ __forceinline__ u64 blend_diff2(u64 dB, u64 sB, const float2* softg)
 }
 
 // Opaque frame (alpha 255 before and after): blend + composite + requantise one colour channel of
-// two rows.  x = fa*T + (255 - fa)*b = fa*(T - b) + 255*b is an integer in [0, 65025].
+// two rows.  The reference's x = fa*T + (255 - fa)*b = 255*b + y with y = fa*(T - b) an integer in
+// [-65025, 65025], so floor(x / 255) = b + floor(y / 255) (numpy) and PIL's rint(x / 255) =
+// b + floor((y + 127.5) / 255).  (y + h) / 255 with h = 0.5 resp. 127.5 is never closer than 0.5 / 255
+// to an integer, so multiplying by fl(1/255) instead (relative error 6e-8, absolute below 2e-5) keeps
+// the floor for either sign of y, and the fma rounded towards -inf adds it to the biased b exactly.
 template <int MODE>
 __device__ __forceinline__ u64 blend_chan(u64 dB, u64 sB, u64 fa, const float2* softg)
 {
-    const u64 kM = bc(kMagic);
-    const u64 x = fma2(fa, blend_diff2<MODE>(dB, sB, softg), fma2(dB, bc(255.0f), bc(kNeg255Magic)));
-    if constexpr (MODE == 18) return fma2(x, bc(kInv255), kM);                    // PIL: floor((x+127)/255) = rint(x/255)
-    else return fma2_rm(x, bc(kInv255), kM);                                      // numpy: floor(x/255)
+    const u64 yh = fma2(fa, blend_diff2<MODE>(dB, sB, softg), bc(MODE == 18 ? 127.5f : 0.5f));
+    return fma2_rm(yh, bc(kInv255), dB);
 }
 
 struct RowPairState { u64 c[4]; };   // r, g, b, a of rows (2p, 2p+1), biased (a is unused on opaque frames)
@@ -406,12 +407,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
 }
 
 constexpr int kMaxStages = 8;   // shared-memory stages of TMA boxes in flight (2, 4 or 8 are used)
-// How a layer reaches a tile (decided per tile by the producer warp):
+// How a layer reaches a tile (decided per tile by k_stack_prep, refined by the producer warp):
 //   kTileEdge      taps gathered through L1 with full bounds / coverage logic (always valid)
 //   kTileInterior  tile fully inside the bbox and every tap inside the source: unchecked L1 gather
 //   kTileTma       taps come from a TMA-staged box, tile fully inside the bbox (the common case)
 //   kTileTmaPart   TMA-staged box, tile partly outside the bbox
-enum { kTileEdge = 0, kTileInterior = 2, kTileTma = 3, kTileTmaPart = 7 };
+//   kTileTmaLut / kTileTmaPartLut   the same for a layer whose opacity needs its table (kLayerLut)
+// Odd codes are the ones that use a TMA stage.
+enum { kTileEdge = 0, kTileTmaLut = 1, kTileInterior = 2, kTileTma = 3, kTileTmaPartLut = 5, kTileTmaPart = 7 };
 
 // cv2's bilinear weights of a sample at (sumx, sumy) (1/1024 px; 5 fractional bits are used), times 32:
 // wt = 32 (32 - fx)(32 - fy) | 32 fx (32 - fy) << 16,  wb = 32 (32 - fx) fy | 32 fx fy << 16  (imgwarp.cpp:
@@ -450,8 +453,9 @@ struct PixelCtx {
 // opacities a few ulps below a fraction of small integers).  Then, with the alpha biased as
 // everything else here (magic + a):   fma.rm(magic + a, c, magic - magic c) = magic + floor(a c),
 // exactly: magic c = 48 m and the addend are representable, the product is exact inside the fma.
-// Layers without such a constant carry a 256-float table in global memory and are walked as
-// kTileEdge, where it is consulted (outside the common path).
+// Layers without such a constant (opacity 0.7 is one) carry their 256-entry table in global memory and
+// travel through tile classes of their own (kTile*Lut), which look the value up; layers with a
+// constant pay nothing for that.
 template <bool OPAQUE, int QUADS, class Slot>
 __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* __restrict__ layers, const Slot& S,
                                            const int* layer_index, const PixelCtx& C,
@@ -470,7 +474,22 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
     uint32_t wt[ROWS], wb[ROWS];   // cv2's 2 x 2 weights, two 16-bit values each: (w00, w01), (w10, w11)
     unsigned ok = (1u << ROWS) - 1u;   // bit q: row q of this thread lies inside the layer's bbox and the frame
     float oc = __int_as_float(info.z); // the layer's opacity constant c (see above)
-    auto staged = [&](auto part_tag) {
+    // A layer whose opacity table is not floor(a c) for any c: take the bilinear alpha here, look the scaled
+    // value v up and give all four taps the alpha v.  The common code below then samples exactly v (the
+    // weights sum to 1024) and, with c = 1, leaves it as it is.  Off the common path: only layers flagged
+    // kLayerLut come here, through their own tile classes.
+    auto apply_table = [&](const float* __restrict__ lut) {
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+            const uint32_t t_ba = __byte_perm(t[k][0], t[k][1], 0x7362), b_ba = __byte_perm(t[k][2], t[k][3], 0x7362);
+            const uint32_t a = __dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, 32u * 512u)) >> 15;
+            const uint32_t v = (uint32_t)__ldg(lut + a) << 24;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[k][j] = (t[k][j] & 0x00FFFFFFu) | v;
+        }
+        oc = 1.0f;
+    };
+    auto staged = [&](auto part_tag, auto lut_tag) {
         const uint32_t pitch = (uint32_t)info.x >> 16, stage = (uint32_t)info.w;
         // Tiles the bbox covers only partly run their own copy of the loop (cls == kTileTmaPart): the box
         // spans the covered part alone, so samples outside it read a dummy address (softg) with weight 0, which
@@ -506,15 +525,20 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
             t[q][3] = lds_u32(a[q] + down[q] + 4);
         }
         mbar_arrive_warp((uint32_t)info.y + 8 * kMaxStages);   // this warp is done with the stage
+        if (decltype(lut_tag)::value) apply_table(layers[*layer_index].lut);
     };
     // (an opaque copy of the info word keeps the compiler from folding this test into the switch over the
     // other classes, which it orders with the common case last)
     uint32_t hot;
     asm("mov.b32 %0, %1;" : "=r"(hot) : "r"(info.x));
     if ((hot & 0x700u) == (uint32_t)kTileTma << 8) {
-        staged(std::false_type{});
+        staged(std::false_type{}, std::false_type{});
     } else if (cls == kTileTmaPart) {
-        staged(std::true_type{});
+        staged(std::true_type{}, std::false_type{});
+    } else if (cls == kTileTmaLut) {
+        staged(std::false_type{}, std::true_type{});
+    } else if (cls == kTileTmaPartLut) {
+        staged(std::true_type{}, std::true_type{});
     } else if (cls == kTileInterior) {
         const DevLayer& L = layers[*layer_index];
         const uint8_t* __restrict__ src = L.src;
@@ -550,21 +574,7 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
             }
             tap_weights(sumx, sumy, wt[k], wb[k]);
         }
-        if (L.flags & kLayerLut) {
-            // Rare: this layer's opacity table is not floor(a c) for any c.  Take the bilinear alpha here,
-            // look the scaled value v up and give all four taps the alpha v: the common code below then
-            // samples exactly v (the weights sum to 1024) and, with c = 1, leaves it as it is.
-            const float* __restrict__ lut = L.lut;
-#pragma unroll
-            for (int k = 0; k < ROWS; ++k) {
-                const uint32_t t_ba = __byte_perm(t[k][0], t[k][1], 0x7362), b_ba = __byte_perm(t[k][2], t[k][3], 0x7362);
-                const uint32_t a = __dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, 32u * 512u)) >> 15;
-                const uint32_t v = (uint32_t)__ldg(lut + a) << 24;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) t[k][j] = (t[k][j] & 0x00FFFFFFu) | v;
-            }
-            oc = 1.0f;
-        }
+        if (L.flags & kLayerLut) apply_table(L.lut);
     }
 
     // ---- cv2's fixed-point bilinear: out = (sum w p + 512) >> 10 -------------------------------

@@ -346,8 +346,9 @@ k_stack_frames(const __grid_constant__ FramesParams P)
                 my_c = (nx_e.x >> 8) & 7;
                 my_org = make_int2((int)(short)(nx_e.y & 0xFFFF), nx_e.y >> 16);
                 if (lane >= n_act) { my_li = 0; my_c = kTileEdge; }
-                // the opacity table of a flagged layer is consulted in the general path only
-                if (s_cull[my_li][15] & kLayerLut) my_c = kTileEdge;
+                // a layer whose opacity needs its table travels through the classes that consult it
+                if (s_cull[my_li][15] & kLayerLut)
+                    my_c = my_c == kTileTma ? kTileTmaLut : my_c == kTileTmaPart ? kTileTmaPartLut : kTileEdge;
                 base = 0;
                 first = true;
                 have_tile = n_act > 0 || P.force_units;   // a tile no layer touches was finished by k_stack_prep
@@ -396,10 +397,10 @@ k_stack_frames(const __grid_constant__ FramesParams P)
             //      one (background only).  Lane base + s owns slot s. ---------------------------------------
             const int n_here = min(kWsSlots, n_act - base);
             const bool mine = lane >= base && lane < base + n_here;
-            const unsigned want = __ballot_sync(0xFFFFFFFFu, mine && (my_c & 3) == kTileTma);
+            const unsigned want = __ballot_sync(0xFFFFFFFFu, mine && (my_c & 1));
             const int my_g = g + __popc(want & ((1u << lane) - 1u));   // ring position of this lane's box
             const int32_t* C = s_cull[my_li];
-            if (mine && (my_c & 3) == kTileTma)
+            if (mine && (my_c & 1))
                 s_req[my_g & (kWsUnits * kWsSlots - 1)] = make_int4(C[18], C[6] * C[7] * 4, my_org.x, my_org.y);
             g += __popc(want);
             __syncwarp();

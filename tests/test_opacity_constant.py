@@ -73,3 +73,21 @@ def test_awkward_opacities_are_flagged_for_the_table_fallback():
             else:
                 near += 1
     assert near > 0
+
+
+def test_blend_tail_floor_division_by_255_is_exact_for_both_signs():
+    """blend_chan (stack_float.cuh): b + floor(y / 255) is taken as fma.rm(y + 0.5, fl32(1/255), magic + b)
+    and PIL's b + rint(y / 255) as fma.rm(y + 127.5, ...), for every integer y = fa (T - b) in
+    [-65025, 65025].  The fma is exact before its single rounding towards -inf, so the claim is
+    floor((y + h) * c) == floor((y + h) / 255) with c = 0x3B808081 = 8421505 / 2^31, checked here in
+    integer arithmetic."""
+    import struct
+    c_num = 8421505
+    assert struct.unpack("<f", struct.pack("<I", 0x3B808081))[0] == c_num / 2.0 ** 31 == float(np.float32(1.0) / np.float32(255.0))
+    y = np.arange(-65025, 65026, dtype=np.int64)
+    # h = 0.5: (2 y + 1) c_num / 2^32
+    assert np.array_equal(((2 * y + 1) * c_num) >> 32, y // 255)
+    # h = 127.5: (2 y + 255) c_num / 2^32  ==  floor(y / 255 + 0.5)
+    assert np.array_equal(((2 * y + 255) * c_num) >> 32, (2 * y + 255) // 510)
+    # and the biased sum stays inside [2^23, 2^24), where the fp32 grid is the integers
+    assert MAGIC - 256 >= 2 ** 23 and MAGIC + 255 + 256 < 2 ** 24
