@@ -1,31 +1,38 @@
 #!/usr/bin/env python
 """Benchmark of the per-frame compositing path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--quick]
 
-Workload (BASELINE.json configs[1], scene S2 of SURVEY.md 8d): a 3840x2160 composition of 16
+Headline workload (BASELINE.json configs[1], scene S2 of SURVEY.md 8d): a 3840x2160 composition of 16
 synthetic 1920x1080 RGBA layers cycling the blend modes, rotating / scaling, with animated opacity.
-One STEP = one pass of the hot path over one batch of synthetic input = rendering the whole 5 s @
-30 fps timeline (150 frames): batched keyframe evaluation on the host + one fused kernel launch per
-frame.  Metric: composited frames/sec (whole job, all GPUs).
+One STEP = one pass of the hot path over one batch of synthetic input = rendering 150 frames through
+the public batched renderer (movis_b200.render.render_frames: batched keyframe evaluation on the host,
+one persistent fused kernel launch per run of up to 32 frames).  Metric: composited frames/sec (whole
+job, all GPUs).
 
   value     frames/s with sources resident in HBM and frames left in HBM (device timed, CUDA events)
   e2e       frames/s through the public API with HOST buffers: every step uploads the 16 sources
             from pinned host memory and delivers every finished uint8 frame to pinned host memory
-  roofline  achieved algorithmic GB/s of the fused kernel k_stack_ws (B_frame = 4*W*H + sum 4*w_l*h_l =
-            165 888 000 B, each source texel and each output pixel counted once) / measured HBM peak;
-            `traffic` = dram bytes per launch from the committed ncu capture (profiles/roofline_traffic.json).
-            One launch = one frame.  mvb_composite_frames alternates the frames of a batch between two
-            side streams (forked from / joined into the caller's stream) so that one frame's CTAs fill
-            the SMs the previous frame's last CTAs leave idle; `avg_launch_us` is therefore elapsed
-            time / launches over back-to-back batches (CUDA events on the caller's stream around the
-            fork and the join), and `serial_launch_us` is the same kernel launched one frame at a
-            time on the caller's stream (mvb_composite_stack), for comparison with ncu's durations
-  cpu_baseline  the CPU oracle (a C + OpenMP port of the reference algorithm) on the host cores
+            (movis_b200.render.stream_frames, the loop of Composition._write_video)
+  roofline  achieved algorithmic GB/s of the fused kernel k_stack_frames / measured HBM peak.  One launch
+            = one run of `frames_per_launch` frames; algorithmic bytes per frame B_frame = 4*W*H +
+            sum 4*w_l*h_l = 165 888 000 B (each source texel and each output pixel counted once).  Timed
+            live with CUDA events on the launch stream over prebuilt plans (the events also bracket each
+            run's 100 KB record upload and its preparation kernel k_stack_prep, < 2 % of the run).
+            `traffic` = dram bytes per launch scaled from the committed ncu capture
+            (profiles/roofline_traffic.json; `traffic_source` says so: it is not measured by this run).
+  configs   device frames/s and roofline fraction of the other BASELINE.json configs (S1, S2d, S3, S4 at
+            draft levels 1/2/4, S5), each from a few hundred ms of rendering
+  s5        BASELINE.json configs[4]: the 1800-frame 4K timeline, frame-sharded over the ranks (STRONG
+            scaling: total work fixed): device and delivered frames/s of the whole job
+  cpu_baseline  the reference's algorithm on the host cores (rank 0, N = 1): the real reference when it
+            is importable (/root/reference, build container only), else its C + OpenMP oracle port
 
-Multi-GPU: launched with torchrun, one rank per GPU; each rank renders its own contiguous 150-frame
-range of the timeline (weak scaling); ranks exchange no pixels -- torch.distributed is used only
-for the barrier and the max-over-ranks reduction of the elapsed time.
+Multi-GPU: launched with torchrun, one rank per GPU.  The job is ONE fixed timeline of 150 * N frames
+(the 5 s scene sampled at 30 * N fps); rank r renders the contiguous index range
+render.shard_range(150 N, r, N) of it, so ranks render DIFFERENT frames and per-GPU work is fixed
+(weak scaling).  Ranks exchange no pixels -- torch.distributed is used only for the barrier and the
+max-over-ranks reduction of the elapsed time.
 """
 from __future__ import annotations
 
@@ -49,6 +56,14 @@ FPS = 30.0
 DURATION = 5.0
 FRAMES_PER_STEP = 150
 WORKLOAD = "S2: 3840x2160, 16x(1920x1080 RGBA) layers, 18 blend modes cycling, animated opacity/scale/rotation"
+BG = (0, 0, 0, 255)
+
+
+def bench_config(world: int) -> dict:
+    return {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "fps": FPS,
+            "l2": "inputs larger than L2 (133 MB sources + 33 MB frame per frame; the sources are "
+                  "double-buffered and alternated frame by frame, so no frame finds the previous frame's texels in L2)",
+            "parallelism": f"frame-range sharding x{world} of one timeline (render.shard_range), no collective"}
 
 
 def measured_hbm_peak() -> tuple[float, str]:
@@ -60,13 +75,14 @@ def measured_hbm_peak() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def recorded_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+def recorded_traffic_per_frame():
+    """dram bytes per FRAME of the fused kernel from the committed ncu capture, if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-            return json.load(fh).get("dram_bytes_per_launch")
+            d = json.load(fh)
+            return d.get("dram_bytes_per_frame"), d.get("source")
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -124,7 +140,7 @@ class ClockSampler:
         return out
 
 
-def dist_setup(n_gpus: int):
+def dist_setup():
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -132,8 +148,8 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         from movis_b200.device import bind_host_to_gpu
-        bind_host_to_gpu(local)   # pinned frame buffers on the GPU's own NUMA node
         torch.cuda.set_device(local)
+        dist_setup.binding = bind_host_to_gpu(local)   # pinned frame buffers on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(0)
@@ -170,91 +186,174 @@ def pinned_sources():
     return out
 
 
-def rank_times(rank: int) -> np.ndarray:
-    """Rank r renders the contiguous frame range [150 r, 150 (r + 1)) of the 30 fps timeline,
-    wrapped into the 5 s scene (weak scaling: per-GPU work is fixed)."""
-    k = np.arange(rank * FRAMES_PER_STEP, (rank + 1) * FRAMES_PER_STEP)
-    return (k % int(DURATION * FPS)) / FPS
+def timeline(world: int, rank: int) -> np.ndarray:
+    """This rank's share of the job: ONE timeline of 150 * world frames (the 5 s scene at 30 * world
+    fps), contiguous index range render.shard_range(150 world, rank, world)."""
+    from movis_b200.render import shard_range
+    total = FRAMES_PER_STEP * world
+    mine = shard_range(total, rank, world)
+    return np.asarray(mine, dtype=np.float64) / (FPS * world)
 
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (device frames/s + roofline fraction, a few hundred ms each)
+# ---------------------------------------------------------------------------------------------
+
+def s3_bytes_per_frame() -> int:
+    # steady state: the three effect outputs are static images (cached once per range), so per frame the
+    # inner frame reads its colour background + them and is written; the parent reads it + its own
+    # background and is written (SURVEY 8d without the once-per-range effect stages)
+    inner = 4 * 1920 * 1080
+    outs = 4 * (482 * 482 + 510 * 510 + 482 * 482)
+    outer = 4 * 3840 * 2160
+    return (inner + outs + inner) + (outer + inner + outer)
+
+
+def s4_bytes_per_frame(level: int) -> int:
+    return 4 * (3840 // level) * (2160 // level) + 2 * 33177600   # frame + keyed 4K frame + the bg region sampled
+
+
+def s5_bytes_per_frame() -> int:
+    from movis_b200 import scenes
+    inner = 4 * 1920 * 1080
+    outs = 4 * (482 * 482 + 510 * 510 + 482 * 482)
+    return scenes.s2_bytes_per_frame(1) + (inner + outs + inner) + inner + 33177600 + 6 * inner
+
+
+def time_scene(comp, times: np.ndarray, level: int = 1, reps: int = 2) -> float:
+    """Seconds per frame of `comp` over `times` through Composition.render_frames (second pass onwards)."""
+    import torch
+    with comp.preview(level=level):
+        out = comp.render_frames(times, bg_color=BG)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = comp.render_frames(times, bg_color=BG, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+    del out
+    return e0.elapsed_time(e1) / 1e3 / (reps * len(times))
+
+
+def other_configs(peak: float) -> dict:
+    import torch
+    import movis_b200 as mv
+    from movis_b200 import scenes
+    from movis_b200.contrib.segmentation import ChromaKey
+    full = np.arange(0, DURATION, 1 / FPS)
+    out = {}
+
+    def record(name, spf, nbytes, frames, note=""):
+        out[name] = {"device_frames_per_s": 1.0 / spf, "us_per_frame": spf * 1e6, "algorithmic_bytes_per_frame": nbytes,
+                     "achieved_GBps": nbytes / spf / 1e9, "roofline_frac": nbytes / spf / 1e9 / peak, "frames": frames}
+        if note:
+            out[name]["note"] = note
+
+    comp = scenes.build_s1(mv)
+    record("S1 (configs[0]: 1080p, bg + 8 rotating layers)", time_scene(comp, full, reps=4), scenes.s1_bytes_per_frame(), len(full))
+    comp = scenes.build_s2d(mv)
+    record("S2d (dense: 17 full-frame 4K layers)", time_scene(comp, full[:30]), scenes.s2d_bytes_per_frame(), 30)
+    del comp
+    torch.cuda.empty_cache()
+    comp = scenes.build_s3(mv)
+    record("S3 (configs[2]: nested 1080p comp with blur / shadow / glow in a 4K parent)", time_scene(comp, full[:60]),
+           s3_bytes_per_frame(), 60, "effect outputs are static: computed once per range")
+    comp = scenes.build_s4(mv, ChromaKey)
+    for level in (1, 2, 4):
+        record(f"S4 L={level} (configs[3]: chroma-keyed 4K sequence over a 4.2K background)", time_scene(comp, full[:48], level=level),
+               s4_bytes_per_frame(level), 48, "the chroma key runs as its own pass per distinct sequence frame (8 of them, cached)")
+    del comp
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------
 
 def run_product(args) -> dict:
     import torch
     import movis_b200 as mv
-    from movis_b200 import scenes
-    from movis_b200.render import launch_plan, plan_range, stream_frames
+    from movis_b200 import _native, scenes
+    from movis_b200.render import launch_plan, plan_range, render_frames, shard_range, stream_frames
 
-    rank, local, world = dist_setup(args.gpus)
+    rank, local, world = dist_setup()
+    lib = _native.lib()
     sources = pinned_sources()
     comp = scenes.build_s2(mv, div=1, variant=0, sources=sources)
-    times = rank_times(rank)
+    times = timeline(world, rank)
     H, W = comp.frame_shape()
-    bg = (0, 0, 0, 255)
     frames = torch.empty((FRAMES_PER_STEP, H, W, 4), dtype=torch.uint8, device="cuda")
 
-    # Two device copies of the sources, alternated frame by frame, so no frame finds the previous
-    # frame's texels in L2 (inputs per frame 133 MB + 33 MB out > 126 MB L2 anyway).
-    plan0 = plan_range(comp, times)
+    # Two device copies of the sources, alternated frame by frame through render_frames' plan hook, so no
+    # frame finds the previous frame's texels in L2 (inputs per frame 133 MB + 33 MB out > 126 MB L2 anyway).
     base = {int(item.layer.render_device(0.0).data_ptr()): i for i, item in enumerate(comp.layers)}
     twins = [item.layer.render_device(0.0).clone() for item in comp.layers]
 
-    def alternate(plan):
+    def alternate(plan, first_index):
         odd = np.zeros(len(plan.descriptors), dtype=bool)
-        for f in range(1, plan.n_frames, 2):
-            odd[plan.offsets[f]:plan.offsets[f + 1]] = True
+        for f in range(plan.n_frames):
+            if (first_index + f) & 1:
+                odd[plan.offsets[f]:plan.offsets[f + 1]] = True
         src = plan.descriptors["src"]
         for p, i in base.items():
             src[odd & (src == p)] = twins[i].data_ptr()
         return plan
 
-    CHUNK = 30   # frames planned per host call, as Composition.render_frames does it (even: keeps the twin parity)
-
     def step():
-        # host: batched keyframes + affine set-up of a chunk; device: the fused launches of the chunk
-        # before it, so only the first chunk after an idle device is not overlapped
-        for i in range(0, FRAMES_PER_STEP, CHUNK):
-            plan = alternate(plan_range(comp, times[i:i + CHUNK]))
-            launch_plan(plan, frames[i:i + CHUNK], bg)
-        return plan
+        # the public batched path: host plans a chunk (batched keyframes + affine set-up) while the device
+        # renders the one before it
+        render_frames(comp, times, bg_color=BG, out=frames, plan_hook=alternate)
 
     for _ in range(max(args.warmup, 3)):
-        keep = step()
+        step()
     barrier(world)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
+    launches0 = int(lib.mvb_kernel_launches())
     ev0.record()
     for _ in range(args.steps):
-        keep = step()
+        step()
     ev1.record()
     barrier(world)
+    launches = int(lib.mvb_kernel_launches()) - launches0
     elapsed = max_over_ranks(ev0.elapsed_time(ev1) / 1e3, world)
     clocks = sampler.stop() if rank == 0 else {}
     total_frames = world * args.steps * FRAMES_PER_STEP
     value = total_frames / elapsed
-    launches = args.steps * FRAMES_PER_STEP * 2   # per frame: k_stack_tables (cv2 tables) + k_stack_ws
 
-    # --- roofline of the fused kernel: launches only, plan prebuilt, CUDA events on the launch stream
-    plan = alternate(plan_range(comp, times))
-    launch_plan(plan, frames, bg)
+    # --- roofline of the fused kernel: launches only, plans prebuilt, CUDA events on the launch stream
+    from movis_b200.render import PLAN_CHUNK
+    plans = [alternate(plan_range(comp, times[i:i + PLAN_CHUNK]), i) for i in range(0, FRAMES_PER_STEP, PLAN_CHUNK)]
+
+    def launch_all():
+        for k, p in enumerate(plans):
+            launch_plan(p, frames[k * PLAN_CHUNK:k * PLAN_CHUNK + p.n_frames], BG)
+
+    launch_all()
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
+    n0 = int(lib.mvb_kernel_launches())
     k0.record()
     for _ in range(reps):
-        launch_plan(plan, frames, bg)
+        launch_all()
     k1.record()
     torch.cuda.synchronize()
-    launch_s = k0.elapsed_time(k1) / 1e3 / (reps * FRAMES_PER_STEP)
-    # the same launches one at a time on the current stream (no overlap between frames)
-    from movis_b200 import _native
-    lib = _native.lib()
-    bg_arr = np.asarray(bg, dtype=np.uint8)
+    runs = (int(lib.mvb_kernel_launches()) - n0) // 2 // reps      # each run = k_stack_prep + k_stack_frames
+    frame_s = k0.elapsed_time(k1) / 1e3 / (reps * FRAMES_PER_STEP)
+    # the same frames one per call (mvb_composite_stack: a run of one frame each), for comparison with
+    # per-frame launch schemes
+    bg_arr = np.asarray(BG, dtype=np.uint8)
     stream = torch.cuda.current_stream().cuda_stream
+    plan = plans[0]
 
     def serial():
-        for f in range(FRAMES_PER_STEP):
+        for f in range(plan.n_frames):
             d = plan.descriptors[plan.offsets[f]:plan.offsets[f + 1]]
             _native.check(lib.mvb_composite_stack(frames[f].data_ptr(), W, H, frames.stride(1), bg_arr.ctypes.data,
                                                   len(d), d.ctypes.data, 0, stream))
@@ -264,14 +363,19 @@ def run_product(args) -> dict:
     serial()
     k1.record()
     torch.cuda.synchronize()
-    serial_s = k0.elapsed_time(k1) / 1e3 / FRAMES_PER_STEP
+    serial_s = k0.elapsed_time(k1) / 1e3 / plan.n_frames
     b_frame = scenes.s2_bytes_per_frame(1)
     peak, peak_src = measured_hbm_peak()
-    achieved = b_frame / launch_s / 1e9
+    achieved = b_frame / frame_s / 1e9
+    frames_per_launch = FRAMES_PER_STEP / max(runs, 1)
+    traffic_frame, traffic_src = recorded_traffic_per_frame()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(), "kernel": "k_stack_ws",
-                "algorithmic_bytes_per_launch": b_frame, "avg_launch_us": launch_s * 1e6,
-                "serial_launch_us": serial_s * 1e6, "peak_source": peak_src}
+                "traffic": None if traffic_frame is None else traffic_frame * frames_per_launch,
+                "traffic_source": None if traffic_frame is None else f"committed ncu capture, not measured by this run ({traffic_src})",
+                "kernel": "k_stack_frames", "frames_per_launch": frames_per_launch,
+                "algorithmic_bytes_per_launch": b_frame * frames_per_launch, "algorithmic_bytes_per_frame": b_frame,
+                "avg_launch_us": frame_s * frames_per_launch * 1e6, "us_per_frame": frame_s * 1e6,
+                "single_frame_call_us": serial_s * 1e6, "peak_source": peak_src}
 
     # --- e2e: host sources -> device, render, every frame back to pinned host memory ---------------
     h2d = sum(int(s.nbytes) for s in sources)
@@ -283,7 +387,7 @@ def run_product(args) -> dict:
         for item in comp.layers:
             item.layer._device_image = None          # forces the H2D upload of every source
         n = 0
-        for _frame in stream_frames(comp, times, bg_color=bg, batch=10, copy=False):
+        for _frame in stream_frames(comp, times, bg_color=BG, copy=False):
             n += 1
         return n
 
@@ -296,70 +400,147 @@ def run_product(args) -> dict:
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0, world)
     e2e = {"value": world * e2e_steps * FRAMES_PER_STEP / e2e_elapsed, "unit": UNIT,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "d2h_GBps": world * e2e_steps * d2h / e2e_elapsed / 1e9,
            "api": "movis_b200.render.stream_frames (Composition._write_video loop)"}
 
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "fps": FPS,
-                   "l2": "inputs larger than L2 (133 MB sources + 33 MB frame per launch, sources double-buffered)",
-                   "parallelism": f"frame-range sharding x{world}, no collective"},
+        "config": bench_config(world),
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "host_binding": getattr(dist_setup, "binding", None),
     }
-    if rank == 0 and world == 1:
-        result["cpu_baseline"] = cpu_baseline(sample_frames=6)
+
+    if not args.quick:
+        # --- BASELINE.json configs[4]: the 1800-frame timeline, frame-sharded (strong scaling) ---------
+        frames = None
+        twins.clear()
+        comp = None
+        torch.cuda.empty_cache()
+        result["s5"] = run_s5(world, rank)
+        if rank == 0 and world == 1:
+            result["configs"] = other_configs(peak)
+            result["cpu_baseline"] = cpu_baseline()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
     return result if rank == 0 else {}
 
 
-def cpu_baseline(sample_frames: int) -> dict:
-    """The oracle port of the reference algorithm on the host cores, on every 25th frame of the
-    same timeline (bounded sample), keyframes evaluated per frame like the reference does."""
+def run_s5(world: int, rank: int) -> dict:
+    import torch
     import movis_b200 as mv
     from movis_b200 import scenes
-    from oracle import oracle as O
-    from oracle import scene_eval
-    # torchrun exports OMP_NUM_THREADS=1; the baseline is meant to use every host thread we may run on
-    O.set_num_threads(len(os.sched_getaffinity(0)))
-    comp = scenes.build_s2(mv, div=1, variant=0)
-    times = (np.arange(sample_frames) * 25 % 150) / FPS
-    scene_eval.render(comp, float(times[0]), (0, 0, 0, 255))  # warm up (page in sources)
+    from movis_b200.contrib.segmentation import ChromaKey
+    from movis_b200.render import render_frames, shard_range, stream_frames
+    N = 1800
+    comp = scenes.build_s5(mv, ChromaKey)
+    mine = shard_range(N, rank, world)
+    times = np.asarray(mine, dtype=np.float64) / FPS
+    for _ in stream_frames(comp, times[:16], bg_color=BG, copy=False):   # warm-up: uploads, effect caches
+        pass
+    out = torch.empty((60,) + comp.frame_shape() + (4,), dtype=torch.uint8, device="cuda")
+    barrier(world)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(0, len(times), 60):
+        chunk = times[i:i + 60]
+        render_frames(comp, chunk, bg_color=BG, out=out[:len(chunk)])
+    ev1.record()
+    barrier(world)
+    device_s = max_over_ranks(ev0.elapsed_time(ev1) / 1e3, world)
+    del out
+    barrier(world)
     t0 = time.perf_counter()
-    for t in times:
-        scene_eval.render(comp, float(t), (0, 0, 0, 255))
-    dt = time.perf_counter() - t0
-    return {"value": sample_frames / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-            "sample": f"{sample_frames} frames of the S2 timeline (every 25th), C oracle with OpenMP on all host threads"}
+    n = 0
+    for _ in stream_frames(comp, times, bg_color=BG, copy=False):
+        n += 1
+    barrier(world)
+    delivered_s = max_over_ranks(time.perf_counter() - t0, world)
+    peak, _ = measured_hbm_peak()
+    b = s5_bytes_per_frame()
+    return {"workload": "S5 (configs[4]): 60 s 4K 30 fps, 1800 frames, 24 layers + nested effects + keyed sequence",
+            "scaling": "strong", "frames": N, "frames_per_rank": len(mine),
+            "device_frames_per_s": N / device_s, "delivered_frames_per_s": N / delivered_s,
+            "algorithmic_bytes_per_frame": b, "roofline_frac_per_gpu": b * N / device_s / 1e9 / peak / world}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's CPU implementation of the path
+# ---------------------------------------------------------------------------------------------
+
+SAMPLE_TIMES = (0.5, 2.5, 4.5)   # the bounded sample of the S2 timeline the CPU arms render per step
+
+
+class CpuArm:
+    """The reference's own per-frame render of S2 on the host cores: the unmodified reference when it is
+    importable (oracle.ref_harness, build container only -- /root/reference does not travel to the GPU
+    box), else the C + OpenMP oracle port of the same algorithm on all host threads.  The scene is built
+    ONCE; every step renders the same time samples."""
+
+    def __init__(self) -> None:
+        import movis_b200 as mv
+        from movis_b200 import scenes
+        from oracle import oracle as O
+        from oracle import ref_harness, scene_eval
+        self.kind, self.cores = "port", len(os.sched_getaffinity(0))
+        if ref_harness.available():
+            ref = ref_harness.import_reference()
+            self.kind = "reference"
+            comp = scenes.build_s2(ref, div=1, variant=0)
+            self.render = lambda t: comp(float(t), bg_color=BG)
+            try:
+                import cv2
+                self.cores = cv2.getNumThreads()   # numpy and PIL are single-threaded; cv2 uses its pool
+            except Exception:
+                self.cores = 1
+            self.how = "unmodified reference (numpy / cv2 / PIL), one process, cv2 default threads"
+        else:
+            # torchrun exports OMP_NUM_THREADS=1; the baseline is meant to use every host thread we may run on
+            O.set_num_threads(self.cores)
+            self.cores = O.num_threads()
+            comp = scenes.build_s2(mv, div=1, variant=0)
+            self.render = lambda t: scene_eval.render(comp, float(t), BG)
+            self.how = "C + OpenMP oracle port of the reference algorithm on all host threads"
+        self.render(SAMPLE_TIMES[0])   # warm up (page in the sources)
+
+    def step(self) -> float:
+        t0 = time.perf_counter()
+        for t in SAMPLE_TIMES:
+            self.render(t)
+        return time.perf_counter() - t0
+
+    def describe(self) -> str:
+        return f"{len(SAMPLE_TIMES)} frames of the S2 timeline (t = {', '.join(str(t) for t in SAMPLE_TIMES)} s) per step; {self.how}"
+
+
+def cpu_baseline() -> dict:
+    arm = CpuArm()
+    reps = 1 if arm.kind == "reference" else 4
+    dt = sum(arm.step() for _ in range(reps))
+    return {"value": reps * len(SAMPLE_TIMES) / dt, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()}
 
 
 def run_reference(args) -> dict:
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot
-    travel to the GPU box) on all host threads.  Each step is a bounded sample of the workload."""
+    """--impl reference: the reference's CPU implementation of the path, same metric and config as the
+    product arm; each step renders a bounded sample of the workload (the same frames every step, scene
+    built once outside the timed loop)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return {}
-    per_step = 2
-    base = None
-    for _ in range(max(args.warmup, 1)):
-        base = cpu_baseline(per_step)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        base = cpu_baseline(per_step)
-    dt = time.perf_counter() - t0
-    # cpu_baseline() renders per_step + 1 frames (one warm-up frame) per call
-    value = args.steps * (per_step + 1) / dt
-    cb = dict(base)
-    cb["value"] = value
-    cb["sample"] = f"{per_step + 1} frames of the S2 timeline per step; " + cb["sample"]
+    arm = CpuArm()
+    for _ in range(max(args.warmup, 1) if arm.kind == "port" else 0):
+        arm.step()
+    steps = args.steps if arm.kind == "port" else min(args.steps, 2)   # the real reference needs ~8 s per 4K frame
+    dt = sum(arm.step() for _ in range(steps))
+    value = steps * len(SAMPLE_TIMES) / dt
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+        "steps": steps, "warmup": max(args.warmup, 1) if arm.kind == "port" else 0, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": per_step + 1, "fps": FPS},
-        "cpu_baseline": cb,
+        "config": bench_config(int(os.environ.get("WORLD_SIZE", "1"))),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -371,6 +552,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (skip S5, the other configs and the CPU baseline)")
     args = ap.parse_args()
     result = run_reference(args) if args.impl == "reference" else run_product(args)
     if result:

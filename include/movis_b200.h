@@ -83,6 +83,11 @@ MVB_API int mvb_abi_version(void);
 /* 0 when the current CUDA device can run this library (compute capability 10.x), else an error. */
 MVB_API int mvb_device_check(void);
 
+/* Number of kernels this library has launched in this process so far (all entry points, all threads).
+ * Diagnostic: lets a benchmark report how many of the library's kernels ran inside a timed region
+ * without guessing at the launch structure. */
+MVB_API uint64_t mvb_kernel_launches(void);
+
 /* Upper bound on n_layers for a single mvb_composite_stack launch (longer stacks are chunked
  * internally; this is informational). */
 MVB_API int mvb_max_layers_per_launch(void);

@@ -30,7 +30,7 @@ assert LAYER_DTYPE.itemsize == 104
 
 # every symbol include/movis_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "mvb_last_error", "mvb_abi_version", "mvb_device_check", "mvb_max_layers_per_launch",
+    "mvb_last_error", "mvb_abi_version", "mvb_device_check", "mvb_kernel_launches", "mvb_max_layers_per_launch",
     "mvb_composite_stack", "mvb_composite_frames", "mvb_warp_affine_rgba8", "mvb_alpha_composite",
     "mvb_blur_ksize", "mvb_gaussian_weights_q8", "mvb_effect_blur_scratch_bytes",
     "mvb_effect_blur_rgba8", "mvb_effect_drop_shadow_rgba8", "mvb_effect_chroma_key_rgba8",
@@ -62,6 +62,7 @@ def lib():
     L.mvb_abi_version.restype = i32
     L.mvb_device_check.restype = i32
     L.mvb_max_layers_per_launch.restype = i32
+    L.mvb_kernel_launches.restype = C.c_uint64
     L.mvb_composite_stack.argtypes = [vp, i32, i32, i64, u8p, i32, vp, i32, vp]
     L.mvb_composite_frames.argtypes = [i32, vp, i32, i32, i64, u8p, vp, vp, i32, vp]
     L.mvb_warp_affine_rgba8.argtypes = [vp, i32, i32, i64, vp, i32, i32, i64, vp, vp]

@@ -452,6 +452,7 @@ static int launch_run(int nF, void* const* frames, const int32_t* beg, const int
         const long long blocks = (long long)nL * T.tab_blocks + (long long)nF * ((T.n_tiles + 7) / 8);
         if (blocks > 0x7FFFFFFFll) return set_error(MVB_ERR_UNSUPPORTED, "run too large");
         k_stack_prep<<<(unsigned)blocks, 256, 0, stream>>>(T);
+        count_launches(1);
     }
 
     P.frames = reinterpret_cast<const FrameRec*>(C->dev + off_frames);
@@ -491,19 +492,22 @@ static int launch_run(int nF, void* const* frames, const int32_t* beg, const int
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, kernels[variant]) != cudaSuccess) return check_launch("mvb_composite_frames");
         Gm.static_smem = (int)fa.sharedSizeBytes;
-        Gm.dyn_max = 4 * kMaxStageBytes;
+        Gm.dyn_max = 6 * kMaxStageBytes;
         // static + dynamic shared memory can exceed 48 KB: opt in once
         cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, Gm.dyn_max);
         cudaDeviceGetAttribute(&Gm.n_sm, cudaDevAttrMultiProcessorCount, dev);
         Gm.dev = dev;
     }
-    // four stages when they leave room for the CTAs per SM the register budget allows (3 with 4 rows, 2 with 8)
+    // as many stages as leave room for the CTAs per SM the register budget allows (3 with 4 rows, 2 with 8);
+    // (228 KB per SM, 1 KB reserved per CTA)
     const int per_cta = (rows == 8 ? 113 : 75) * 1024 - Gm.static_smem - 1024;
-    P.stages_log2 = 4 * P.stage_bytes <= per_cta ? 2 : 1;
-    static const int force_stages = env_int("MVB_STAGES_LOG2", 0);   // diagnostics: 1..3
-    if (force_stages >= 1 && force_stages <= 3 && ((size_t)P.stage_bytes << force_stages) <= (size_t)Gm.dyn_max)
-        P.stages_log2 = force_stages;
-    const int smem = P.stage_bytes << P.stages_log2;
+    static const int force_stages = env_int("MVB_STAGES", 0);   // diagnostics: 2..8
+    int stages = P.stage_bytes > 0 ? per_cta / P.stage_bytes : kMaxStages;
+    if (force_stages) stages = force_stages;
+    stages = std::max(2, std::min(stages, kMaxStages));
+    while (stages > 2 && stages * P.stage_bytes > Gm.dyn_max) --stages;
+    P.stages = stages;
+    const int smem = P.stage_bytes * P.stages;
     if (Gm.occ_smem != smem) {
         int v = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernels[variant], kWsThreads, (size_t)smem);
@@ -527,6 +531,7 @@ static int launch_run(int nF, void* const* frames, const int32_t* beg, const int
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernels[variant], P);
+    count_launches(1);
     return check_launch("mvb_composite_frames");
 }
 
@@ -625,6 +630,7 @@ extern "C" int mvb_warp_affine_rgba8(const void* src, int32_t sw, int32_t sh, in
     k_warp_affine<<<grid, 256, 0, (cudaStream_t)stream>>>(
         static_cast<const uint8_t*>(src), sw, sh, (int)sstride, static_cast<uint8_t*>(dst), dw, dh,
         (int)dstride, m[0], m[1], m[2], m[3], m[4], m[5]);
+    count_launches(1);
     return check_launch("mvb_warp_affine_rgba8");
 }
 
@@ -658,5 +664,6 @@ extern "C" int mvb_alpha_composite(void* bg, int32_t bw, int32_t bh, int64_t bst
     const bool lum = matte_mode == MVB_MATTE_LUMINANCE;
     const dim3 grid(((lum ? bw : P.w) + 31) / 32, ((lum ? bh : P.h) + 7) / 8);
     k_alpha_composite<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    count_launches(1);
     return check_launch("mvb_alpha_composite");
 }

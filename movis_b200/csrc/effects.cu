@@ -571,10 +571,14 @@ extern "C" int mvb_effect_blur_rgba8(const void* src, int32_t w, int32_t h, int6
     if (tiled) {
         const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);
         k_blur_h_rgba_tiled<<<dim3((W2 + kBlurHOut - 1) / kBlurHOut, h), 256, (n_in + k + 12) * 4, st>>>(P);
+        count_launches(1);
         k_blur_v_rgba_tiled<<<dim3((W2 + 31) / 32, (H2 + 31) / 32), 256, 0, st>>>(P);
+        count_launches(1);
     } else {
         k_blur_h_rgba<<<dim3((W2 + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
+        count_launches(1);
         k_blur_v_rgba<<<dim3((W2 + 31) / 32, (H2 + 7) / 8), 256, 0, st>>>(P);
+        count_launches(1);
     }
     return check_launch("mvb_effect_blur_rgba8");
 }
@@ -610,10 +614,14 @@ extern "C" int mvb_effect_drop_shadow_rgba8(const void* src, int32_t w, int32_t 
         if (k <= kTiledMaxK) {
             const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);
             k_blur_h_alpha_tiled<<<dim3((Ws + kBlurHOut - 1) / kBlurHOut, h), 256, (n_in + k + 12) * 4, st>>>(P);
+            count_launches(1);
             k_blur_v_alpha_tiled<<<dim3((Ws + 31) / 32, (Hs + 31) / 32), 256, 0, st>>>(P);
+            count_launches(1);
         } else {
             k_blur_h_alpha<<<dim3((Ws + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
+            count_launches(1);
             k_blur_v_alpha<<<dim3((Ws + 31) / 32, (Hs + 7) / 8), 256, 0, st>>>(P);
+            count_launches(1);
         }
         S.a1 = plane;
     }
@@ -627,6 +635,7 @@ extern "C" int mvb_effect_drop_shadow_rgba8(const void* src, int32_t w, int32_t 
     S.color = (uint32_t)color[0] | ((uint32_t)color[1] << 8) | ((uint32_t)color[2] << 16);
     std::memcpy(S.lut, opacity_lut, 256);
     k_drop_shadow<<<dim3((Wn + 31) / 32, (Hn + 7) / 8), 256, 0, st>>>(S);
+    count_launches(1);
     return check_launch("mvb_effect_drop_shadow_rgba8");
 }
 
@@ -646,6 +655,7 @@ static int launch_pointwise(PointParams& P, const void* src, int w, int h, int64
     const int blocks = (int)std::min<long long>((work + 255) / 256, 148 * 8);
     if (vec) k_pointwise<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
     else k_pointwise<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+    count_launches(1);
     return check_launch(what);
 }
 
@@ -752,6 +762,7 @@ extern "C" int mvb_source_stripe_rgba8(void* dst, int32_t w, int32_t h, int64_t 
     P.width = params[4]; P.phase = params[5]; P.edge0 = params[6]; P.span = params[7];
     for (int k = 0; k < 4; k++) { P.c1[k] = params[8 + k]; P.c2[k] = params[12 + k]; }
     k_stripe<<<dim3((unsigned)((w + 63) / 64), (unsigned)((h + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(P);
+    count_launches(1);
     return check_launch("mvb_source_stripe_rgba8");
 }
 

@@ -1,4 +1,5 @@
 // host_util.cu -- error state, device check and host-side fp64 set-up for the C ABI.
+#include <atomic>
 #include <cstdio>
 #include <string>
 
@@ -41,6 +42,10 @@ int require_device()
     return cached_rc;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
 int check_launch(const char* what)
 {
     cudaError_t e = cudaGetLastError();
@@ -70,3 +75,4 @@ void invert_affine_cv(const double M[6], double m[6])
 extern "C" const char* mvb_last_error(void) { return mvb::g_last_error.c_str(); }
 extern "C" int mvb_abi_version(void) { return MVB_ABI_VERSION; }
 extern "C" int mvb_device_check(void) { return mvb::require_device(); }
+extern "C" uint64_t mvb_kernel_launches(void) { return mvb::g_launches.load(std::memory_order_relaxed); }

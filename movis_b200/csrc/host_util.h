@@ -11,6 +11,9 @@ int set_error(int code, const char* msg);
 // MVB_OK when the current device is an sm_100-class GPU (cached per device), else an error.
 int require_device();
 
+// Adds n to the process-wide count of kernels this library has launched (mvb_kernel_launches).
+void count_launches(int n);
+
 // cudaGetLastError() after a launch -> MVB_OK / MVB_ERR_CUDA.
 int check_launch(const char* what);
 

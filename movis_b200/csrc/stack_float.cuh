@@ -336,31 +336,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 // Blocks until the phase with the given parity has completed.  The common case is one try_wait and a
 // branch.  mbarrier.try_wait suspends the thread in the barrier unit for a hardware-defined time, so a
-// longer wait is a short loop of probes (two instructions each).  It is bounded by WALL TIME
-// (%globaltimer, looked at every 2^18 probes), not by a spin count: a slow but live run -- under a
-// debugger, a profiler replay or time slicing -- is left alone, and only a wait that has made no
-// progress for 20 s (a broken descriptor, i.e. a bug) traps instead of hanging the device.
+// longer wait is a run of probes: eight straight ones (most waits in this kernel are for data that is
+// about to land), then a counted loop.  It is bounded by WALL TIME (%globaltimer, looked at every 2^18
+// probes), not by a spin count: a slow but live run -- under a debugger, a profiler replay or time
+// slicing -- is left alone, and only a wait that has made no progress for 20 s (a broken descriptor,
+// i.e. a bug) traps instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+#define MVB_PROBE "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MVB_DONE;\n"
     asm volatile(
         "{\n"
         ".reg .pred p, q;\n"
         ".reg .u32 n;\n"
         ".reg .u64 t0, t1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MVB_DONE;\n"
+        MVB_PROBE MVB_PROBE MVB_PROBE MVB_PROBE MVB_PROBE MVB_PROBE MVB_PROBE MVB_PROBE MVB_PROBE
         "mov.u64 t0, %%globaltimer;\n"
         "MVB_AGAIN:\n"
         "mov.u32 n, 0;\n"
         "MVB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MVB_DONE;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MVB_DONE;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MVB_DONE;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MVB_DONE;\n"
+        MVB_PROBE MVB_PROBE MVB_PROBE MVB_PROBE
         "add.u32 n, n, 1;\n"
         "setp.lt.u32 q, n, 65536;\n"
         "@q bra MVB_WAIT;\n"
@@ -371,6 +365,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "bra MVB_AGAIN;\n"
         "MVB_DONE:\n"
         "}" ::"r"(bar), "r"(parity) : "memory");
+#undef MVB_PROBE
 }
 // One non-blocking probe of the phase with the given parity.
 __device__ __forceinline__ int mbar_test(uint32_t bar, uint32_t parity)

@@ -33,7 +33,10 @@
 
 namespace mvb {
 
-constexpr int kWsConsumers = 8;                   // 8 warps x ROWS rows = one tile
+#ifndef MVB_CONSUMERS
+#define MVB_CONSUMERS 8
+#endif
+constexpr int kWsConsumers = MVB_CONSUMERS;       // consumer warps x ROWS rows = one tile
 constexpr int kWsThreads = (kWsConsumers + 1) * 32;
 constexpr int kWsSlots = 8;                       // layers per unit
 #ifndef MVB_UNITS
@@ -215,7 +218,7 @@ struct FramesParams {
     int32_t keep_frame;        // start from the pixels in the frames (continuing a stack of more than kMaxLayers layers)
     int32_t tab_w, tab_h;
     int32_t stage_bytes;       // bytes of one shared-memory stage (the largest box of this run)
-    int32_t stages_log2;       // 1..3: two, four or eight stages in flight
+    int32_t stages;            // 2..kMaxStages stages in flight
     int32_t tiles_x, n_tiles;  // per frame
     int32_t tile_stride;       // int2 entries per tile record
     int32_t force_units;       // diagnostics: walk background-only tiles too
@@ -229,7 +232,10 @@ struct FramesParams {
 // fourth channel and both "over" operators use their general forms (over_numpy_rows / over_pil_rows).
 // ROWS: rows per thread (4 or 8); the tile is 32 x (8 * ROWS).
 template <bool OPAQUE, int ROWS>
-__global__ void __launch_bounds__(kWsThreads, ROWS == 4 ? 3 : 2)
+#ifndef MVB_MINBLOCKS
+#define MVB_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kWsThreads, ROWS == 4 ? MVB_MINBLOCKS : 2)
 k_stack_frames(const __grid_constant__ FramesParams P)
 {
     constexpr int QUADS = ROWS / 4, PAIRS = ROWS / 2, TILE_H = kWsConsumers * ROWS;
@@ -245,7 +251,7 @@ k_stack_frames(const __grid_constant__ FramesParams P)
     const uint32_t bar_full = smem_addr(&s_bar[0]), bar_empty = smem_addr(&s_bar[kMaxStages]);
     const uint32_t unit_full = smem_addr(&s_bar[2 * kMaxStages]), unit_empty = smem_addr(&s_bar[2 * kMaxStages + kWsUnits]);
     const uint32_t stage0 = smem_addr(s_stage);
-    const int ns_log2 = P.stages_log2, ns_mask = (1 << ns_log2) - 1;
+    const int ns = P.stages;
 
     if (tid == 0) {
 #pragma unroll
@@ -260,7 +266,7 @@ k_stack_frames(const __grid_constant__ FramesParams P)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 256) s_softg[tid] = make_float2(g_softg[2 * tid], g_softg[2 * tid + 1]);
+    if (tid < 256) s_softg[tid] = make_float2(g_softg[2 * tid], g_softg[2 * tid + 1]);   // (kWsThreads >= 256)
     __syncthreads();
 
     if (warp == kWsConsumers) {
@@ -272,23 +278,33 @@ k_stack_frames(const __grid_constant__ FramesParams P)
         // outstanding).  Lane st < stages owns stage st: it requests the boxes q = st (mod stages) in order, as soon as the producer passes by and the
         // stage has come free -- the lanes work side by side, so one pass costs one barrier probe + one
         // TMA issue however many stages came free.
-        int my_head = lane;   // lanes < stages: next request number for the lane's stage
+        int my_head = lane;   // lanes < stages: next request number for the lane's stage (lane + my_k * stages)
+        int my_k = 0;         // how many boxes the lane has requested: the stage's phase count
+        int g_stage = 0, g_round = 0;   // stage and use count of request number g
         asm volatile("griddepcontrol.wait;" ::: "memory");   // k_stack_prep's results are complete and visible
         auto service = [&]() {
-            if (lane <= ns_mask) {
+            if (lane < ns) {
                 while (my_head < g) {
-                    if (my_head > ns_mask && !mbar_test(bar_empty + 8 * lane, ((my_head >> ns_log2) - 1) & 1)) break;
+                    if (my_k > 0 && !mbar_test(bar_empty + 8 * lane, (my_k - 1) & 1)) break;
                     const int4 r = s_req[my_head & (kWsUnits * kWsSlots - 1)];
                     mbar_arrive_expect_tx(bar_full + 8 * lane, (uint32_t)r.y);
                     tma_load_box(stage0 + lane * P.stage_bytes, &P.maps[r.x], r.z, r.w, bar_full + 8 * lane);
-                    my_head += ns_mask + 1;
+                    my_head += ns;
+                    ++my_k;
                 }
             }
             __syncwarp();
         };
-        // the oldest request still waiting for its stage (INT_MAX: none)
-        auto oldest_pending = [&]() {
-            return __reduce_min_sync(0xFFFFFFFFu, (lane <= ns_mask && my_head < g) ? my_head : 0x7FFFFFFF);
+        // Waits for the stage of the oldest request that is still queued; false: nothing is queued.
+        auto wait_for_oldest = [&]() {
+            const bool pend = lane < ns && my_head < g;
+            const int head = __reduce_min_sync(0xFFFFFFFFu, pend ? my_head : 0x7FFFFFFF);
+            if (head == 0x7FFFFFFF) return false;
+            const int owner = __ffs((int)__ballot_sync(0xFFFFFFFFu, pend && my_head == head)) - 1;
+            const int k = __shfl_sync(0xFFFFFFFFu, my_k, owner);   // > 0: a first use never waits
+            mbar_wait(bar_empty + 8 * owner, (k - 1) & 1);
+            __syncwarp();
+            return true;
         };
         // Items are handed out through a counter in the run's scratch (zeroed by the upload): a static
         // round-robin pins a CTA to the same few tile columns of every frame (its stride and the tiles
@@ -358,11 +374,7 @@ k_stack_frames(const __grid_constant__ FramesParams P)
                 if (!have_tile) continue;
             }
             if (!have_tile && stop_sent) {
-                const int head = oldest_pending();
-                if (head == 0x7FFFFFFF) break;   // everything requested: done
-                // the consumers still wait for boxes whose stage is busy
-                mbar_wait(bar_empty + 8 * (head & ns_mask), ((head >> ns_log2) - 1) & 1);
-                __syncwarp();
+                if (!wait_for_oldest()) break;   // everything requested: done (else the consumers still wait for boxes)
                 continue;
             }
             // ---- the next unit (or the stop mark) needs a free unit buffer ---------------------------------
@@ -376,10 +388,10 @@ k_stack_frames(const __grid_constant__ FramesParams P)
             if (!free_) {
                 // Nothing can proceed without an event: wait for the one needed first.  A queued box gates the
                 // consumers sooner than a unit that is four units ahead of them.
-                const int head = oldest_pending();
-                if (head != 0x7FFFFFFF) mbar_wait(bar_empty + 8 * (head & ns_mask), ((head >> ns_log2) - 1) & 1);
-                else mbar_wait(ubar_empty, ubar_par);
-                __syncwarp();
+                if (!wait_for_oldest()) {
+                    mbar_wait(ubar_empty, ubar_par);
+                    __syncwarp();
+                }
                 continue;
             }
             UnitMem<ROWS>& U = s_unit[ub];
@@ -398,11 +410,16 @@ k_stack_frames(const __grid_constant__ FramesParams P)
             const int n_here = min(kWsSlots, n_act - base);
             const bool mine = lane >= base && lane < base + n_here;
             const unsigned want = __ballot_sync(0xFFFFFFFFu, mine && (my_c & 1));
-            const int my_g = g + __popc(want & ((1u << lane) - 1u));   // ring position of this lane's box
+            const int my_off = __popc(want & ((1u << lane) - 1u));
+            const int my_g = g + my_off;   // request number of this lane's box, its stage and that stage's use count
+            int my_st = g_stage + my_off, my_rd = g_round;
+            while (my_st >= ns) { my_st -= ns; ++my_rd; }
             const int32_t* C = s_cull[my_li];
             if (mine && (my_c & 1))
                 s_req[my_g & (kWsUnits * kWsSlots - 1)] = make_int4(C[18], C[6] * C[7] * 4, my_org.x, my_org.y);
             g += __popc(want);
+            g_stage += __popc(want);
+            while (g_stage >= ns) { g_stage -= ns; ++g_round; }
             __syncwarp();
             service();
             // the info word, and two bulk copies of the layer's tables restricted to the tile (columns
@@ -416,10 +433,10 @@ k_stack_frames(const __grid_constant__ FramesParams P)
             if (mine) {
                 const int pitch = C[6] * 4;   // box_w px
                 UnitSlot<ROWS>& S = U.slot[lane - base];
-                S.info = make_int4(C[14] | ((my_c & 7) << 8) | (((my_g >> ns_log2) & 1) << 11) | (pitch << 16),
-                                   (int)(bar_full + 8 * (my_g & ns_mask)),
+                S.info = make_int4(C[14] | ((my_c & 7) << 8) | ((my_rd & 1) << 11) | (pitch << 16),
+                                   (int)(bar_full + 8 * my_st),
                                    C[16],
-                                   (int)(stage0 + (my_g & ns_mask) * P.stage_bytes - my_org.y * pitch - my_org.x * 4));
+                                   (int)(stage0 + my_st * P.stage_bytes - my_org.y * pitch - my_org.x * 4));
                 U.layer[lane - base] = my_li;
                 const int2* tab = fr_tab + (size_t)my_li * (size_t)(P.tab_w + P.tab_h);
                 bulk_load(smem_addr(S.col), tab + tx0, sizeof(int2) * kTileW, ubar);

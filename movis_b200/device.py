@@ -25,24 +25,56 @@ def require_cuda() -> None:
         raise NoDeviceError("movis_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
 
 
-def bind_host_to_gpu(device_index: int) -> list[int]:
-    """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA
-    node), so that pinned staging buffers allocated afterwards live next to that GPU's PCIe root.
-    Matters when several ranks deliver frames to host memory at once.  Returns the CPU list used
-    (empty when NVML or a usable CPU set is not available -- then nothing is changed)."""
-    import os
+def gpu_numa_node(device_index: int) -> int:
+    """NUMA node of the GPU's PCIe slot from /sys/bus/pci/devices/<bdf>/numa_node (-1: unknown or not
+    exposed, e.g. on a single-node virtual machine).  NVML's CPU affinity is useless on such hosts
+    (every CPU is reported local to every GPU); sysfs is the kernel's own view."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
-        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
-        usable = sorted(ideal & os.sched_getaffinity(0))
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            return int(fh.read().strip())
+    except Exception:
+        return -1
+
+
+def _parse_cpulist(text: str) -> list[int]:
+    cpus: list[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the GPU's NUMA node and prefer that node for its memory,
+    so that pinned staging buffers allocated afterwards live next to that GPU's PCIe root.  Matters when
+    several ranks deliver frames to host memory at once.  Returns what was done:
+    ``{"numa_node": n, "cpus": [...], "mempolicy": bool}``; with an unknown node (``-1``) or a node
+    without usable CPUs nothing is changed."""
+    import ctypes
+    import os
+    info = {"numa_node": gpu_numa_node(device_index), "cpus": [], "mempolicy": False}
+    node = info["numa_node"]
+    if node < 0:
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            usable = sorted(set(_parse_cpulist(fh.read())) & os.sched_getaffinity(0))
         if usable:
             os.sched_setaffinity(0, usable)
-        return usable
+            info["cpus"] = usable
+        # set_mempolicy(MPOL_PREFERRED, {node}): new pages (incl. the driver's pinned allocations made on
+        # behalf of this thread) come from the GPU's node when it has room
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL(None, use_errno=True)
+        if node < 64 and libc.syscall(238, 1, ctypes.byref(mask), 65) == 0:   # x86-64: __NR_set_mempolicy
+            info["mempolicy"] = True
     except Exception:
-        return []
+        pass
+    return info
 
 
 def stream_ptr() -> int:

@@ -156,11 +156,15 @@ def launch_plan(plan: RangePlan, out: torch.Tensor, bg_color) -> None:
         plan.descriptors.ctypes.data if len(plan.descriptors) else None, 0, stream_ptr()))
 
 
-def render_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 255), out: torch.Tensor | None = None):
+def render_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 255), out: torch.Tensor | None = None,
+                  plan_hook=None):
     """Render every time in ``times`` into a CUDA tensor ``(N, H // L, W // L, 4)``.
 
     Times outside ``[0, duration)`` are not allowed here (``Composition.__call__`` returns None
-    for them).  Asynchronous: returns after the launches are enqueued on the current stream."""
+    for them).  Asynchronous: returns after the launches are enqueued on the current stream.
+    ``plan_hook(plan, first_frame_index) -> plan``, if given, sees every chunk's ``RangePlan`` before
+    it is launched (instrumentation: e.g. the benchmark redirects descriptors to twin copies of the
+    sources)."""
     require_cuda()
     times = np.asarray(times, dtype=np.float64)
     assert times.ndim == 1
@@ -178,6 +182,8 @@ def render_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 
     # instead of their sum.
     for i in range(0, len(times), PLAN_CHUNK):
         plan = plan_range(comp, times[i:i + PLAN_CHUNK])
+        if plan_hook is not None:
+            plan = plan_hook(plan, i)
         launch_plan(plan, out[i:i + PLAN_CHUNK], bg_color)
     return out
 
@@ -186,12 +192,14 @@ def stream_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 
                   copy: bool = True) -> Iterator[np.ndarray]:
     """Yield host uint8 frames for ``times`` in order.
 
-    With ``copy=False`` the yielded arrays are views into the pinned staging buffers and stay
-    valid only until the generator is advanced ``batch`` more frames (enough for a writer that
-    consumes each frame immediately, like the reference's ``writer.append_data`` loop).
+    With ``copy=False`` the yielded array is a view into a pinned staging buffer and is valid ONLY
+    until the next frame is requested from the generator (asking for the next frame may start the
+    copy that overwrites it).  That is enough for a writer that consumes each frame immediately, like
+    the reference's ``writer.append_data`` loop; keep ``copy=True`` to hold on to frames.
 
-    Two device batches and two pinned host batches alternate: while batch i is copied to the
-    host on a side stream and consumed by the caller, batch i + 1 is planned and rendered."""
+    Two device batches and two pinned host batches alternate: while batch i is copied to the host on
+    a side stream (one cudaMemcpyAsync per batch) and consumed by the caller, batch i + 1 is planned
+    and rendered."""
     require_cuda()
     times = np.asarray(times, dtype=np.float64)
     H, W = comp.frame_shape()
