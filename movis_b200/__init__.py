@@ -20,6 +20,7 @@ from .enum import (AttributeType, BlendingMode, Direction, Easing, MatteMode,  #
 from .imgproc import alpha_composite  # noqa
 from .layer.protocol import AUDIO_SAMPLING_RATE  # noqa
 from .motion import Motion  # noqa
+from .ops import crop  # noqa
 from .transform import Transform  # noqa
 from .util import to_rgb  # noqa
 

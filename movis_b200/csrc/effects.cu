@@ -12,6 +12,7 @@
 //            (alpha rows outside the source contribute 0), with the Glow composite fused in.
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -464,17 +465,26 @@ static void host_hsv_tables(HsvTables& t)
     }
 }
 
+// cv2's division tables, uploaded once per device per process.  The copy comes from pageable memory on
+// the legacy default stream and may return before the DMA has landed, while the kernels that read the
+// tables run on non-blocking streams: the device is synchronised once, right after the copy, under a
+// process-wide lock (no other thread can launch a reader before the flag is set).
 static int upload_hsv_tables()
 {
-    static thread_local int uploaded_dev = -1;
+    static std::mutex mu;
+    static uint64_t uploaded_mask[2] = {0, 0};   // devices 0..127
     int dev = -1;
     cudaGetDevice(&dev);
-    if (dev == uploaded_dev) return MVB_OK;
-    HsvTables t;
-    host_hsv_tables(t);
+    if (dev < 0 || dev >= 128) return set_error(MVB_ERR_NO_DEVICE, "no current CUDA device");
+    std::lock_guard<std::mutex> lock(mu);
+    if (uploaded_mask[dev >> 6] >> (dev & 63) & 1) return MVB_OK;
+    static HsvTables t;
+    static bool built = false;
+    if (!built) { host_hsv_tables(t); built = true; }
     cudaError_t e = cudaMemcpyToSymbol(g_hsv, &t, sizeof t);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return set_error(MVB_ERR_CUDA, cudaGetErrorString(e));
-    uploaded_dev = dev;
+    uploaded_mask[dev >> 6] |= 1ull << (dev & 63);
     return MVB_OK;
 }
 

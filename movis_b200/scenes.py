@@ -299,3 +299,59 @@ def build_fuzz(mv: Any, seed: int, size=(160, 90), n_layers: int = 18, duration:
         if i % 4 == 1:
             _ramp(item.opacity, 0.0, duration, 0.1, 0.9, "ease_out3")
     return comp
+
+
+# ---------------------------------------------------------------------------------------------
+# ops.crop views and matte layers under animated transforms
+# ---------------------------------------------------------------------------------------------
+
+def build_ops(mv: Any, div: int = 1, duration: float = 2.0):
+    """A cropped image (a strided view of its source), an AlphaMatte with animated opacity, a
+    LuminanceMatte whose target is itself a crop, and a crop of a nested composition: each rotated /
+    scaled / blended inside one parent (ops.py:280-321, layer/layer_ops.py:55-109)."""
+    W, H = 320 // div, 200 // div
+    comp = mv.layer.Composition(size=(W, H), duration=duration)
+    comp.add_layer(mv.layer.Image(synthetic_rgba(6000, H, W, alpha="opaque")), name="bg")
+    big = mv.layer.Image(synthetic_rgba(6001, 180 // div, 240 // div, alpha="random", rim=10 // div))
+    cr = mv.crop(big, (30 // div, 20 // div, 150 // div, 110 // div))
+    item = comp.add_layer(cr, name="crop", position=(110 / div, 80 / div), scale=(1.2, 0.9), opacity=0.8,
+                          blending_mode="screen")
+    _ramp(item.rotation, 0.0, duration, -25.0, 40.0, "ease_in_out2")
+    mh, mw = 96 // div, 128 // div
+    # Read-only, like an image decoded from a file (media.py:111): the reference's matte layers composite
+    # INTO the array their mask layer returns unless it is read-only (imgproc.py:263), and a writable mask
+    # would change from call to call.
+    mask_px = synthetic_rgba(6002, mh, mw, alpha="random", rim=6 // div)
+    mask_px.flags.writeable = False
+    mask = mv.layer.Image(mask_px)
+    target = mv.layer.Image(synthetic_rgba(6003, mh, mw, alpha="random"))
+    am = mv.layer.AlphaMatte(mask, target, opacity=0.6, blending_mode="multiply")
+    _ramp(am.opacity, 0.0, duration, 0.2, 1.0)
+    item = comp.add_layer(am, name="alpha_matte", position=(220 / div, 70 / div), blending_mode="overlay")
+    _ramp(item.rotation, 0.0, duration, 10.0, -50.0)
+    _ramp(item.scale, 0.0, duration, (0.8, 0.8), (1.3, 1.3))
+    wide = mv.layer.Image(synthetic_rgba(6004, mh + 20 // div, mw + 40 // div, alpha="random"))
+    lm = mv.layer.LuminanceMatte(mask, mv.crop(wide, (17 // div, 9 // div, mw, mh)))
+    item = comp.add_layer(lm, name="lum_matte", position=(90 / div, 150 / div), rotation=15.0, opacity=0.9)
+    _ramp(item.position, 0.0, duration, (90 / div, 150 / div), (140 / div, 130 / div))
+    inner = build_fuzz(mv, seed=5, size=(120 // div, 90 // div), n_layers=6, duration=duration)
+    item = comp.add_layer(mv.crop(inner, (25 // div, 15 // div, 80 // div, 60 // div)), name="crop_comp",
+                          position=(240 / div, 150 / div), blending_mode="difference")
+    _ramp(item.rotation, 0.0, duration, 0.0, 90.0)
+    return comp
+
+
+# ---------------------------------------------------------------------------------------------
+# one FULL-SIZE frame of every BASELINE.json config, pinned against the reference by digest
+# (oracle/gen_golden.py writes manifest.json["full_size_digests"]; tests/test_gpu_scenes.py asserts them)
+# ---------------------------------------------------------------------------------------------
+
+def full_size_shots(mv: Any, chroma_key_cls: Any):
+    """Yields (tag, build() -> composition, time); background colour (0, 0, 0, 255), draft level 1."""
+    yield "s1", (lambda: build_s1(mv)), 2.5
+    yield "s2v0", (lambda: build_s2(mv, variant=0)), 2.1
+    yield "s2v2", (lambda: build_s2(mv, variant=2)), 3.3
+    yield "s2d", (lambda: build_s2d(mv)), 1.0
+    yield "s3", (lambda: build_s3(mv)), 1.7
+    yield "s4", (lambda: build_s4(mv, chroma_key_cls, n_seq=2)), 0.04
+    yield "s5", (lambda: build_s5(mv, chroma_key_cls, n_seq=2)), 31.0

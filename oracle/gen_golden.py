@@ -50,13 +50,56 @@ def gen_stripe(mv) -> None:
     save("stripe", **out)
 
 
+def gen_ops(mv) -> None:
+    """ops.crop + AlphaMatte / LuminanceMatte under transforms (scenes.build_ops), frames of the reference."""
+    out = {}
+    comp = scenes.build_ops(mv)
+    times = [0.0, 0.9, 1.7]
+    out["times"] = np.asarray(times)
+    for t in times:
+        out[f"frame_{t:.3f}"] = comp(t)
+    out["frame_opaque_0.900"] = comp(0.9, bg_color=(5, 6, 7, 255))
+    comp2 = scenes.build_ops(mv, div=2)
+    with comp2.preview(level=2):
+        out["frame_div2_L2"] = comp2(1.3)
+    # the layers on their own (strided views / matte images as the reference hands them to the stack)
+    for name in ("crop", "alpha_matte", "lum_matte", "crop_comp"):
+        out[f"layer_{name}"] = np.ascontiguousarray(comp[name].layer(0.9))
+    save("ops", **out)
+
+
+def gen_full_size(mv) -> None:
+    """sha256 of one FULL-SIZE frame of every BASELINE.json config, rendered by the reference itself
+    (scenes.full_size_shots; 1 - 20 s per frame).  Only the digests are stored: the tests render the
+    same frame on the GPU and compare hashes, so the frames need not be committed."""
+    import time
+    from movis.contrib.segmentation import ChromaKey
+    path = os.path.join(OUT, "manifest.json")
+    with open(path) as fh:
+        manifest = json.load(fh)
+    out = manifest.setdefault("full_size_digests", {})
+    for tag, build, t in scenes.full_size_shots(mv, ChromaKey):
+        t0 = time.perf_counter()
+        frame = np.asarray(build()(t, bg_color=(0, 0, 0, 255)))
+        out[tag] = {"time": t, "shape": list(frame.shape), "sha256": sha(frame)}
+        print(f"  {tag}: {frame.shape} {time.perf_counter() - t0:.1f} s  {out[tag]['sha256'][:16]}")
+    with open(path, "w") as fh:
+        json.dump(manifest, fh, indent=1, sort_keys=True)
+
+
 def main() -> None:
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     mv = import_reference()
     import sys
+    if "fullsize" in sys.argv[1:]:   # only the full-size digests (merged into manifest.json)
+        gen_full_size(mv)
+        return
     if "stripe" in sys.argv[1:]:   # only this file (the others are unchanged)
         gen_stripe(mv)
+        return
+    if "ops" in sys.argv[1:]:
+        gen_ops(mv)
         return
     import cv2
     import PIL
@@ -269,7 +312,14 @@ def main() -> None:
           (0, 0, 0, 255), store=False)
     save("scene_frames", **frames)
     gen_stripe(mv)
+    gen_ops(mv)
+    try:
+        with open(os.path.join(OUT, "manifest.json")) as fh:
+            previous = json.load(fh)
+    except Exception:
+        previous = {}
     manifest = {
+        "full_size_digests": previous.get("full_size_digests", {}),
         "reference": "rezoo/movis 0.7.1 (/root/reference, unmodified; Qt/imageio/audio modules stubbed)",
         "numpy": np.__version__, "opencv": cv2.__version__, "pillow": PIL.__version__,
         "digests": digests,

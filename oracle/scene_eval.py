@@ -53,27 +53,43 @@ def apply_effect(effect, image: np.ndarray, t: float) -> np.ndarray:
     return effect(image, t)
 
 
+def source_image(layer, layer_time: float) -> np.ndarray | None:
+    """A layer's own image at its local time, through oracle operators only (never the product's
+    device path): nested compositions, matte layers, crops and stripes are evaluated here; plain
+    sources (Image, ImageSequence, foreign callables) are host arrays already."""
+    if _is_composition(layer):
+        return render(layer, layer_time)  # nested comps use their own preview level and bg 0
+    n = _name(layer)
+    if n == "AlphaMatte":
+        return _alpha_matte(layer, layer_time)
+    if n == "LuminanceMatte":
+        return _luminance_matte(layer, layer_time)
+    if n == "Stripe":
+        return _stripe(layer, layer_time)
+    if n == "_CropLayer":
+        return _crop(layer, layer_time)
+    return layer(layer_time)
+
+
 def layer_image(item, time: float) -> np.ndarray | None:
     """LayerItem.__call__ (composition.py:822-831)."""
     layer_time = time - item.offset
     if not item.visible:
         return None
-    layer = item.layer
-    if _is_composition(layer):
-        frame = render(layer, layer_time)  # nested comps use their own preview level and bg 0
-    elif _name(layer) == "AlphaMatte":
-        frame = _alpha_matte(layer, layer_time)
-    elif _name(layer) == "LuminanceMatte":
-        frame = _luminance_matte(layer, layer_time)
-    elif _name(layer) == "Stripe":
-        frame = _stripe(layer, layer_time)
-    else:
-        frame = layer(layer_time)
+    frame = source_image(item.layer, layer_time)
     if frame is None:
         return None
     for e in item.effects:
         frame = apply_effect(e, frame, layer_time)
     return frame
+
+
+def _crop(layer, t):  # ops.py:280-296
+    img = source_image(layer.layer, t)
+    if img is None:
+        return None
+    x, y, w, h = layer.rect
+    return img[y:y + h, x:x + w]
 
 
 def _stripe(layer, t):  # layer/texture.py:159-191
@@ -85,7 +101,7 @@ def _stripe(layer, t):  # layer/texture.py:159-191
 
 
 def _sub(layer, t):
-    return render(layer, t) if _is_composition(layer) else layer(t)
+    return source_image(layer, t)
 
 
 def _alpha_matte(layer, t):  # layer/layer_ops.py:55-67

@@ -164,6 +164,13 @@ def test_matte_layers(mv):                                     # tests/layer/tes
     lm = mv.layer.LuminanceMatte(mask, target)
     assert np.array_equal(lm(0.0), O.alpha_composite(m, t, matte_mode="luminance", use_pil=False))
     assert am.get_key(0.0) == ((0.6,), True, True) and lm.get_key(0.5) == (True, True)
-    scene = mv.layer.Composition(size=(40, 30), duration=1.0)
-    scene.add_layer(am)
-    assert np.array_equal(scene(0.0)[..., :3] * 0 + 1, np.ones((30, 40, 3), np.uint8))  # renders through the stack
+    # the matte layers as sources of the fused stack: rotated, scaled and blended inside a composition
+    from oracle import scene_eval
+    scene = mv.layer.Composition(size=(64, 48), duration=1.0)
+    scene.add_layer(mv.layer.Image.from_color((64, 48), (90, 120, 30)), opacity=0.7)
+    scene.add_layer(am, position=(30.0, 20.0), rotation=25.0, scale=(1.3, 0.8), blending_mode="screen")
+    scene.add_layer(lm, position=(40.0, 30.0), rotation=-40.0, opacity=0.8)
+    for bg in ((0, 0, 0, 0), (9, 9, 9, 255)):
+        got, want = scene(0.0, bg_color=bg), scene_eval.render(scene, 0.0, bg)
+        assert np.array_equal(got, want), np.abs(got.astype(int) - want).max()
+    assert len(np.unique(scene(0.0))) > 50

@@ -93,6 +93,67 @@ def test_s4_chroma_key_draft_levels_full_size_vs_oracle():
         assert f.shape == (2160 // level, 3840 // level, 4)
 
 
+def test_s2d_dense_full_size_vs_oracle():
+    """17 full-frame 4K layers (integer and fractional translations): the dense variant of configs[1]."""
+    from movis_b200 import scenes
+    mv, _ = _mv()
+    _assert_matches_oracle(scenes.build_s2d(mv, div=1), 1.0, (0, 0, 0, 255))
+
+
+def test_s5_timeline_full_size_vs_oracle():
+    """BASELINE.json configs[4] at full size: three frames of the 60 s / 24-layer timeline (start, middle
+    with every layer visible, last frame)."""
+    from movis_b200 import scenes
+    mv, ChromaKey = _mv()
+    comp = scenes.build_s5(mv, ChromaKey, div=1, n_seq=2)
+    for t in (0.0, 31.0, 1799 / 30.0):
+        _assert_matches_oracle(comp, t, (0, 0, 0, 255))
+
+
+def test_full_size_frames_match_reference_digests():
+    """One FULL-SIZE frame of every BASELINE.json config against the sha256 of the same frame rendered by
+    the unmodified reference (oracle/gen_golden.py fullsize -> manifest.json["full_size_digests"])."""
+    from movis_b200 import scenes
+    mv, ChromaKey = _mv()
+    with open(os.path.join(GOLDEN_DIR, "manifest.json")) as fh:
+        want = json.load(fh)["full_size_digests"]
+    seen = 0
+    for tag, build, t in scenes.full_size_shots(mv, ChromaKey):
+        frame = build()(t, bg_color=(0, 0, 0, 255))
+        assert list(frame.shape) == want[tag]["shape"] and t == want[tag]["time"], tag
+        assert hashlib.sha256(np.ascontiguousarray(frame).tobytes()).hexdigest() == want[tag]["sha256"], tag
+        seen += 1
+    assert seen == len(want) == 7
+
+
+def test_crop_and_matte_layers_in_a_composition_match_reference_golden(golden):
+    """ops.crop (a strided device view), AlphaMatte with animated opacity, LuminanceMatte over a cropped
+    target and a crop of a nested composition, each under animated transforms and blend modes: frames of
+    the reference, the layers' own images, a batched range, a draft level."""
+    import movis_b200 as mv
+    from movis_b200 import scenes
+    from movis_b200.render import render_frames
+    g = golden("ops")
+    comp = scenes.build_ops(mv)
+    for name in ("crop", "alpha_matte", "lum_matte", "crop_comp"):
+        layer = comp[name].layer
+        assert np.array_equal(layer(0.9), g["layer_" + name]), name
+        dev = layer.render_device(0.9)
+        assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), g["layer_" + name]), name
+    crop_dev = comp["crop"].layer.render_device(0.9)
+    assert not crop_dev.is_contiguous() and crop_dev.stride(0) == 240 * 4      # a view: no pixels moved
+    assert comp["crop"].layer.get_key(0.9) == comp["crop"].layer.layer.get_key(0.9) and comp["crop"].layer.duration == 1e6
+    for t in g["times"]:
+        assert np.array_equal(comp(float(t)), g[f"frame_{t:.3f}"]), t
+    assert np.array_equal(comp(0.9, bg_color=(5, 6, 7, 255)), g["frame_opaque_0.900"])
+    batch = render_frames(comp, g["times"], bg_color=(0, 0, 0, 0))
+    for i, t in enumerate(g["times"]):
+        assert np.array_equal(batch[i].cpu().numpy(), g[f"frame_{t:.3f}"]), t
+    comp2 = scenes.build_ops(mv, div=2)
+    with comp2.preview(level=2):
+        assert np.array_equal(comp2(1.3), g["frame_div2_L2"])
+
+
 def test_batched_frames_equal_per_frame_renders():
     import torch
     from movis_b200 import scenes

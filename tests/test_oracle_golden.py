@@ -153,6 +153,22 @@ def test_scene_walker_matches_reference_frames(golden):
     assert n == 74
 
 
+def test_scene_walker_crop_and_matte_layers_match_reference(golden):
+    """ops.crop views and AlphaMatte / LuminanceMatte sources (ops.py:280-296, layer_ops.py:55-109)
+    evaluated by the oracle's scene walker, against frames and layer images of the reference."""
+    import movis_b200 as mv
+    from movis_b200 import scenes
+    g = golden("ops")
+    comp = scenes.build_ops(mv)
+    for name in ("crop", "alpha_matte", "lum_matte", "crop_comp"):
+        assert np.array_equal(scene_eval.source_image(comp[name].layer, 0.9), g["layer_" + name]), name
+    for t in g["times"]:
+        assert np.array_equal(scene_eval.render(comp, float(t), (0, 0, 0, 0)), g[f"frame_{t:.3f}"]), t
+    assert np.array_equal(scene_eval.render(comp, 0.9, (5, 6, 7, 255)), g["frame_opaque_0.900"])
+    comp2 = scenes.build_ops(mv, div=2)
+    assert np.array_equal(scene_eval.render(comp2, 1.3, (0, 0, 0, 0), preview_level=2), g["frame_div2_L2"])
+
+
 def test_reciprocal_table_division_is_exact():
     """The fused kernel divides by d in 1..256 with umulhi(n << 8, ceil(2^24 / d)) for n <= 65025
     (color_dodge / color_burn / vivid_light, movis_b200/csrc/pixel_math.cuh): exhaustive check."""
