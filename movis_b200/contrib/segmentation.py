@@ -32,6 +32,12 @@ class ChromaKey(DeviceEffectMixin):
         self._lower_color = np.clip(c - spread, 0, 255).astype(np.uint8)
         self._upper_color = np.clip(c + spread, 0, 255).astype(np.uint8)
 
+    def get_key(self, time: float) -> tuple:
+        """The keyed pixels depend on the input image and the constructor arguments only, so equal
+        source frames may share one cached result (the reference's ChromaKey defines no ``get_key`` and its
+        layer cache therefore never hits, composition.py:767-769)."""
+        return (tuple(int(v) for v in self._lower_color), tuple(int(v) for v in self._upper_color))
+
     def apply_device(self, image: torch.Tensor, time: float) -> torch.Tensor:
         ptr, w, h, stride = image_args(image)
         out = empty_image(h, w)

@@ -15,11 +15,13 @@
 #include <mutex>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/movis_b200.h"
 #include "host_util.h"
 #include "pixel_math.cuh"
+#include "chroma_key.cuh"
 
 namespace mvb {
 
@@ -454,6 +456,70 @@ __global__ void __launch_bounds__(256) k_pointwise(const __grid_constant__ Point
     }
 }
 
+// ChromaKey as its own streaming kernel: the range test of chroma_key.cuh on 128-bit vectors.  Persistent
+// CTAs walk the image 512 vectors at a time (two per thread, 256 apart) and load the next pair before
+// they key the current one, so every thread keeps four loads in flight; the vector index is split into
+// (row, column) by a multiply-high with the host's reciprocal of the row length.
+struct ChromaParams {
+    const uint8_t* src;
+    uint8_t* dst;
+    int32_t w, h, sstride, dstride;
+    uint32_t per_row, total;      // vectors per row, vectors in the image
+    uint32_t rcp_mul, rcp_shift;  // i / per_row == umulhi(i, rcp_mul) >> rcp_shift for i < total
+    ChromaTables tab;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_chroma_key(const __grid_constant__ ChromaParams P)
+{
+    __shared__ uint32_t s_sv[256], s_hq[256];
+    s_sv[threadIdx.x] = P.tab.sv[threadIdx.x];
+    s_hq[threadIdx.x] = P.tab.hq[threadIdx.x];
+    __syncthreads();
+    typedef typename std::conditional<VEC == 4, uint4, uint32_t>::type Vec;
+    auto locate = [&](uint32_t i, int64_t& so, int64_t& dof) {
+        const uint32_t y = __umulhi(i, P.rcp_mul) >> P.rcp_shift, x = i - y * P.per_row;
+        so = (int64_t)y * P.sstride + (int64_t)x * (4 * VEC);
+        dof = (int64_t)y * P.dstride + (int64_t)x * (4 * VEC);
+    };
+    auto key = [&](uint32_t p) { return (p & 0x00FFFFFFu) | (chroma_in_range(p, s_sv, s_hq) ? 0u : 0xFF000000u); };
+    const uint32_t step = gridDim.x * 512u;
+    uint32_t i = blockIdx.x * 512u + threadIdx.x;
+    Vec cur[2], nxt[2];
+    int64_t dcur[2], dnxt[2];
+    auto fetch = [&](uint32_t at, Vec (&v)[2], int64_t (&d)[2]) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            d[k] = -1;
+            if (at + 256u * k < P.total) {
+                int64_t so;
+                locate(at + 256u * k, so, d[k]);
+                v[k] = __ldcs(reinterpret_cast<const Vec*>(P.src + so));
+            }
+        }
+    };
+    if (i < P.total) fetch(i, cur, dcur);
+    while (i < P.total) {
+        const uint32_t in = i + step;
+        dnxt[0] = dnxt[1] = -1;
+        if (in < P.total && in > i) fetch(in, nxt, dnxt);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (dcur[k] < 0) continue;
+            if constexpr (VEC == 4) {
+                const uint4 o = make_uint4(key(cur[k].x), key(cur[k].y), key(cur[k].z), key(cur[k].w));
+                *reinterpret_cast<uint4*>(P.dst + dcur[k]) = o;
+            } else {
+                *reinterpret_cast<uint32_t*>(P.dst + dcur[k]) = key(cur[k]);
+            }
+        }
+        if (in <= i) break;   // (index overflow guard)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { cur[k] = nxt[k]; dcur[k] = dnxt[k]; }
+        i = in;
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------
 
 static void host_hsv_tables(HsvTables& t)
@@ -674,12 +740,48 @@ extern "C" int mvb_effect_chroma_key_rgba8(const void* src, int32_t w, int32_t h
                                            mvb_stream_t stream)
 {
     if (!lo || !hi) return set_error(MVB_ERR_INVALID_ARG, "bounds are null");
-    PointParams P;
-    std::memset(&P, 0, sizeof P);
-    P.op = 0;
-    std::memcpy(P.lo, lo, 3);
-    std::memcpy(P.hi, hi, 3);
-    return launch_pointwise(P, src, w, h, sstride, dst, dstride, stream, "mvb_effect_chroma_key_rgba8");
+    // the bounds tables of the last key used by this thread (an effect instance keeps its key for life)
+    static thread_local ChromaParams C;
+    static thread_local uint8_t c_lo[3], c_hi[3];
+    static thread_local int c_state = 0;   // 0: nothing cached, 1: tables valid, -1: this key needs the full conversion
+    if (c_state == 0 || std::memcmp(c_lo, lo, 3) || std::memcmp(c_hi, hi, 3)) {
+        c_state = build_chroma_tables(lo, hi, C.tab) ? 1 : -1;
+        std::memcpy(c_lo, lo, 3);
+        std::memcpy(c_hi, hi, 3);
+    }
+    if (c_state < 0) {
+        PointParams P;
+        std::memset(&P, 0, sizeof P);
+        P.op = 0;
+        std::memcpy(P.lo, lo, 3);
+        std::memcpy(P.hi, hi, 3);
+        return launch_pointwise(P, src, w, h, sstride, dst, dstride, stream, "mvb_effect_chroma_key_rgba8");
+    }
+    if (int rc = require_device()) return rc;
+    if (int rc = check_rgba(src, w, h, sstride, "src")) return rc;
+    if (int rc = check_rgba(dst, w, h, dstride, "dst")) return rc;
+    C.src = static_cast<const uint8_t*>(src);
+    C.dst = static_cast<uint8_t*>(dst);
+    C.w = w; C.h = h; C.sstride = (int32_t)sstride; C.dstride = (int32_t)dstride;
+    const bool vec = !((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
+                        (uintptr_t)sstride | (uintptr_t)dstride) & 15) && !(w & 3);
+    const uint64_t per_row = vec ? (uint64_t)w / 4 : (uint64_t)w, total = per_row * (uint64_t)h;
+    if (total >= (1ull << 31)) return set_error(MVB_ERR_UNSUPPORTED, "image too large");
+    C.per_row = (uint32_t)per_row;
+    C.total = (uint32_t)total;
+    // floor(i / d) = (i * m) >> (32 + s) with m = ceil(2^(32+s) / d), exact for i < 2^31 when s = ceil(log2 d)
+    uint32_t sh = 0;
+    while ((1ull << sh) < per_row) ++sh;
+    C.rcp_shift = sh;
+    C.rcp_mul = (uint32_t)((((1ull << (32 + sh)) + per_row - 1) / per_row) & 0xFFFFFFFFull);
+    if (per_row == 1) { C.rcp_mul = 0xFFFFFFFFu; C.rcp_shift = 0; }
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 511) / 512, (uint64_t)n_sm * 6);
+    if (vec) k_chroma_key<4><<<grid, 256, 0, (cudaStream_t)stream>>>(C);
+    else k_chroma_key<1><<<grid, 256, 0, (cudaStream_t)stream>>>(C);
+    count_launches(1);
+    return check_launch("mvb_effect_chroma_key_rgba8");
 }
 
 extern "C" int mvb_effect_fill_color_rgba8(const void* src, int32_t w, int32_t h, int64_t sstride, void* dst,

@@ -511,7 +511,9 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
             down[q] = pitch;
             if (PART && !(ok >> q & 1)) { a[q] = smem_addr(softg); down[q] = 0u; wt[q] = wb[q] = 0u; }
         }
+#ifndef MVB_DIAG_NOWAIT   // (diagnostic build: how fast the consumers are when they never wait for a box)
         mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
+#endif
 #pragma unroll
         for (int q = 0; q < ROWS; ++q) {
             t[q][0] = lds_u32(a[q]);
@@ -599,7 +601,11 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
     }
 
     // ---- blend, in the code specialised for this layer's mode ------------------------------------
+#ifdef MVB_DIAG_MODE0      // (diagnostic build: every layer blends as NORMAL)
+    switch (0) {
+#else
     switch (info.x & 255) {
+#endif
 #define MVB_ROWS(M) case M: blend_rows<M, OPAQUE, PAIRS>(d, s, fa, softg, ok); break;
         MVB_ROWS(0) MVB_ROWS(1) MVB_ROWS(2) MVB_ROWS(3) MVB_ROWS(4) MVB_ROWS(5) MVB_ROWS(6) MVB_ROWS(7)
         MVB_ROWS(8) MVB_ROWS(9) MVB_ROWS(10) MVB_ROWS(11) MVB_ROWS(12) MVB_ROWS(13) MVB_ROWS(14)

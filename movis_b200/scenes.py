@@ -219,6 +219,30 @@ def s4_sequence(div: int = 1, n: int = 8) -> list[np.ndarray]:
     return frames
 
 
+class LoopedLayer:
+    """``layer`` repeated end to end for ``duration`` seconds: a foreign layer in the sense of the plugin
+    protocol (``duration``, ``get_key``, ``__call__``).  The frame sequence of S4 lasts 8 frames; looped, the
+    keyed foreground is on screen for the whole timeline ("8 pre-generated 4K frames served
+    at 30 fps").  ``render_device`` is forwarded when the wrapped layer has one, so device-resident
+    sources stay on the device."""
+
+    def __init__(self, layer: Any, duration: float):
+        self.layer = layer
+        self.duration = duration
+        if hasattr(layer, "render_device"):
+            self.render_device = lambda time: (
+                layer.render_device(self._local(time)) if 0 <= time < self.duration else None)
+
+    def _local(self, time: float) -> float:
+        return time % self.layer.duration
+
+    def get_key(self, time: float):
+        return self.layer.get_key(self._local(time)) if 0 <= time < self.duration else None
+
+    def __call__(self, time: float):
+        return self.layer(self._local(time)) if 0 <= time < self.duration else None
+
+
 def build_s4(mv: Any, chroma_key_cls: Any, div: int = 1, duration: float = 5.0, n_seq: int = 8):
     W, H = 3840 // div, 2160 // div
     comp = mv.layer.Composition(size=(W, H), duration=duration)
@@ -226,7 +250,7 @@ def build_s4(mv: Any, chroma_key_cls: Any, div: int = 1, duration: float = 5.0, 
     item = comp.add_layer(mv.layer.Image(bg), name="bg")
     _ramp(item.position, 0.0, duration, (1900 / div, 1080 / div), (1940 / div, 1080 / div))
     seq = mv.layer.ImageSequence.from_files(s4_sequence(div, n_seq), each_duration=1.0 / 30.0)
-    fg = comp.add_layer(seq, name="fg", end_time=duration)
+    fg = comp.add_layer(LoopedLayer(seq, duration), name="fg")
     fg.add_effect(chroma_key_cls())
     return comp
 

@@ -261,6 +261,28 @@ def test_pointwise_effects_vs_oracle_ragged_widths(dev):
     assert (got[:1080, :, 3] == 0).all() and set(np.unique(got[..., 3])) <= {0, 255}
 
 
+def test_chroma_key_every_rgb_colour_vs_oracle(dev):
+    """The ChromaKey kernel tests integer bounds instead of converting to HSV (csrc/chroma_key.cuh): all
+    2^24 colours for keys whose hue range is plain, wraps around red, is empty, is everything, and for
+    grey / dark keys where cv2's division tables clamp."""
+    from movis_b200.contrib.segmentation import ChromaKey
+    from oracle import oracle as O
+    v = np.arange(256, dtype=np.uint8)
+    img = np.empty((4096, 4096, 4), dtype=np.uint8)
+    img[..., 0] = np.tile(v, 16)[None, :]                       # r = x % 256
+    img[..., 1] = np.repeat(v, 16)[:, None]                     # g = y // 16
+    img[..., 2] = (np.arange(4096)[:, None] % 16) * 16 + np.arange(4096)[None, :] // 256   # b
+    img[..., 3] = 77
+    assert len(np.unique(img[..., :3].reshape(-1, 3).astype(np.uint32) @ np.array([1, 256, 65536], np.uint32))) == 1 << 24
+    keys = [((0, 255, 0), (20.0, 0.3, 0.3)), ((255, 0, 0), (40.0, 0.5, 0.5)), ((250, 10, 30), (90.0, 0.2, 0.9)),
+            ((0, 0, 255), (0.0, 0.0, 0.0)), ((10, 200, 220), (360.0, 1.0, 1.0)), ((128, 128, 128), (30.0, 0.1, 0.1)),
+            ((3, 2, 1), (179.0, 0.6, 0.02)), ((255, 255, 0), (1.0, 0.01, 0.01))]
+    for col, rng_ in keys:
+        got = ChromaKey(col, key_color_range=rng_)(img, 0.0)
+        want = O.effect_chroma_key(img, col, rng_)
+        assert np.array_equal(got, want), (col, rng_, int((got[..., 3] != want[..., 3]).sum()))
+
+
 def test_public_alpha_composite_semantics(dev):
     import torch
     import movis_b200 as mv
