@@ -456,7 +456,7 @@ static int launch_run(int nF, void* const* frames, const int32_t* beg, const int
     }
 
     P.frames = reinterpret_cast<const FrameRec*>(C->dev + off_frames);
-    P.next_item = reinterpret_cast<unsigned long long*>(C->dev);
+    P.next_item = reinterpret_cast<float*>(C->dev);
     P.n_frames = nF;
     P.W = W;
     P.H = H;
@@ -517,6 +517,7 @@ static int launch_run(int nF, void* const* frames, const int32_t* beg, const int
     // persistent CTAs: exactly as many as are resident at once (a CTA that has to wait for a slot would
     // start its share of the items when the others are done)
     const long long n_items = (long long)nF * P.n_tiles;
+    if (n_items + (long long)Gm.occ * Gm.n_sm >= (1ll << 24)) return set_error(MVB_ERR_UNSUPPORTED, "run too large");
     const int ctas = (int)std::min<long long>(n_items, (long long)Gm.occ * Gm.n_sm);
     // Programmatic dependent launch: the CTAs may start their prologue while k_stack_prep drains; the
     // producer warps wait for its results (griddepcontrol.wait) before they read the first record.
@@ -566,7 +567,10 @@ static int launch_frames(int n_frames, void* const* frames, int W, int H, int64_
         cnt.clear();
         size_t nL = 0;
         int f1 = f;
-        while (f1 < n_frames && f1 - f < max_run) {
+        // (the run's work counter counts (frame, tile) items exactly up to 2^24: launch_run checks it)
+        const long long tiles_per_frame = (long long)tiles_x * ((H + 31) / 32);
+        const int fit = (int)std::max<long long>(1, ((1ll << 24) - 4096) / std::max<long long>(tiles_per_frame, 1));
+        while (f1 < n_frames && f1 - f < std::min(max_run, fit)) {
             const int c = offsets[f1 + 1] - offsets[f1];
             if (c > kMaxLayers || (f1 > f && (nL + c) * tab_per_layer > max_tab)) break;
             beg.push_back(offsets[f1]);

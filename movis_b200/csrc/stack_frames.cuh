@@ -90,8 +90,8 @@ static_assert(sizeof(FrameRec) == 64, "frame record layout");
 //         the answer iff m a < (k_a + 1) 2^18 for every a.  Otherwise the table itself is stored.
 //   the remaining blocks: one WARP per (frame, tile), lane = layer: cull the layer against the tile and
 //     decide how its taps reach it (kTile*, with the TMA box origin); the layers that touch the tile
-//     are written as a compact list in paint order:  rec[0].x = count, rec[1 + s] = (layer | class << 8,
-//     origin x (16 bits) | origin y << 16).  A tile no layer touches is finished right here (filled with
+//     are written as a compact list in paint order:  rec[0] = (count | frame << 8, tile x0 | y0 << 16),
+//     rec[1 + s] = (layer | class << 8, origin x (16 bits) | origin y << 16).  A tile no layer touches is finished right here (filled with
 //     the background colour, or left alone when the run continues stored frames): k_stack_frames
 //     skips it.
 // ---------------------------------------------------------------------------------------------------
@@ -164,7 +164,7 @@ k_stack_prep(const PrepParams T)
         }
         const unsigned active = __ballot_sync(0xFFFFFFFFu, cls >= 0);
         int2* rec = T.tiles + ((size_t)f * (size_t)T.n_tiles + (size_t)t) * (size_t)T.tile_stride;
-        if (lane == 0) rec[0] = make_int2(__popc(active), 0);
+        if (lane == 0) rec[0] = make_int2(__popc(active) | (f << 8), tx0 | (ty0 << 16));   // count | frame << 8, tile origin
         if (active == 0u && !T.keep_frame && tx0 + lane < T.W) {
             uint8_t* p = F.frame + (size_t)ty0 * (size_t)T.stride + (size_t)(tx0 + lane) * 4;
             const int rows = min(T.tile_h, T.H - ty0);
@@ -223,7 +223,7 @@ struct FramesParams {
     int32_t tile_stride;       // int2 entries per tile record
     int32_t force_units;       // diagnostics: walk background-only tiles too
     int32_t pad_;
-    unsigned long long* next_item;   // work counter of the run (starts at 0; items below gridDim.x are taken statically)
+    float* next_item;          // work counter of the run (starts at 0; items below gridDim.x are taken statically)
     const int2* tiles;         // k_stack_prep's per (frame, tile) lists, frame-major
     alignas(64) CUtensorMap maps[kMaxMaps];   // distinct (source, box) descriptors of the run; DevLayer::map_index
 };
@@ -312,19 +312,25 @@ k_stack_frames(const __grid_constant__ FramesParams P)
         // Items are handed out through a counter in the run's scratch (zeroed by the upload): a static
         // round-robin pins a CTA to the same few tile columns of every frame (its stride and the tiles
         // per row share factors), and the cost of a column -- how many layers cross it -- differs, so the
-        // imbalance would never average out over the run.  The counter is read one item ahead.
-        const long long n_items = (long long)P.n_frames * (long long)P.n_tiles;
-        long long w = blockIdx.x;          // next (frame, tile) item of this CTA
-        long long w_nx = n_items;          // the one after it
+        // imbalance would never average out over the run.  The counter runs TWO items ahead: the atomic
+        // issued while tile k is set up is only looked at when tile k + 1 is, so its round trip (about a
+        // microsecond, a third of a two-layer tile) is never waited for.
+        const int n_items = P.n_frames * P.n_tiles;   // (the host keeps it, plus the grid size, below 2^24)
+        int w = blockIdx.x;                // next (frame, tile) item of this CTA
+        // (The counter is a FLOAT: an integer atom.add in a one-lane branch is compiled to vote + atomic +
+        // shuffle, and the shuffle waits for the result on the spot.  Counts stay below 2^24, so they are exact.)
+        float raw = 0.0f;                  // lane 0: the counter value behind the item after that
         auto take = [&]() {
-            unsigned long long v = 0;
-            if (lane == 0) v = atomicAdd(P.next_item, 1ull);
-            return (long long)__shfl_sync(0xFFFFFFFFu, v, 0) + (long long)gridDim.x;
+            if (lane == 0) asm volatile("atom.global.add.f32 %0, [%1], 0f3F800000;" : "=f"(raw) : "l"(P.next_item) : "memory");
         };
-        w_nx = take();
-        // its list, fetched one tile ahead of its use: header (count) and this lane's entry
+        auto taken = [&]() {
+            const unsigned int v = (unsigned int)__shfl_sync(0xFFFFFFFFu, raw, 0) + gridDim.x;
+            return v < (unsigned int)n_items ? (int)v : n_items;
+        };
+        take();
+        // its list, fetched one tile ahead of its use: header (count, frame, origin) and this lane's entry
         int2 nx_hdr = make_int2(0, 0), nx_e = make_int2(0, 0);
-        auto fetch = [&](long long item) {
+        auto fetch = [&](int item) {
             if (item < n_items) {
                 const int2* rec = P.tiles + (size_t)item * (size_t)P.tile_stride;
                 nx_hdr = __ldg(rec);
@@ -346,7 +352,7 @@ k_stack_frames(const __grid_constant__ FramesParams P)
             service();
             if (!have_tile && w < n_items) {
                 // ---- the next tile --------------------------------------------------------------------
-                const int f = (int)(w / P.n_tiles), t = (int)(w - (long long)f * P.n_tiles);
+                const int f = nx_hdr.x >> 8;
                 if (f != cur_f) {   // entering a new frame: its record and the leading ints of its layers
                     const FrameRec& F = P.frames[f];
                     fr_frame = F.frame; fr_layers = F.layers; fr_tab = F.tab;
@@ -358,9 +364,9 @@ k_stack_frames(const __grid_constant__ FramesParams P)
                     cur_f = f;
                     __syncwarp();
                 }
-                tx0 = (t % P.tiles_x) * kTileW;
-                ty0 = (t / P.tiles_x) * TILE_H;
-                n_act = nx_hdr.x;
+                tx0 = nx_hdr.y & 0xFFFF;
+                ty0 = (int)((unsigned)nx_hdr.y >> 16);
+                n_act = nx_hdr.x & 255;
                 my_li = nx_e.x & 255;
                 my_c = (nx_e.x >> 8) & 7;
                 my_org = make_int2((int)(short)(nx_e.y & 0xFFFF), nx_e.y >> 16);
@@ -371,9 +377,9 @@ k_stack_frames(const __grid_constant__ FramesParams P)
                 base = 0;
                 first = true;
                 have_tile = n_act > 0 || P.force_units;   // a tile no layer touches was finished by k_stack_prep
-                w = w_nx;            // the list of the item after this one is on its way while this one is built,
+                w = taken();         // the list of the item after this one is on its way while this one is built,
                 fetch(w);            // and so is the number of the one after that
-                if (w < n_items) w_nx = take();
+                if (w < n_items) take();
                 if (!have_tile) continue;
             }
             if (!have_tile && stop_sent) {

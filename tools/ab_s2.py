@@ -26,9 +26,20 @@ elif which == "s2d":
     n = 30
 elif which == "s1":
     comp, nbytes = scenes.build_s1(mv), scenes.s1_bytes_per_frame()
+elif which == "s4":
+    comp, nbytes = scenes.build_s4(mv, ChromaKey), 4 * 3840 * 2160 + 2 * 33177600
+    n = 48
+elif which == "s3":
+    comp, nbytes = scenes.build_s3(mv), 0
+    n = 60
+elif which == "s5":
+    comp, nbytes = scenes.build_s5(mv, ChromaKey), 276614192
+    n = 60
 else:
     raise SystemExit("unknown scene")
 times = np.arange(n) / 30.0
+if which == "s5":
+    times = times * 30.0   # spread over the 60 s timeline
 H, W = comp.frame_shape()
 frames = torch.empty((n, H, W, 4), dtype=torch.uint8, device="cuda")
 bg = (0, 0, 0, 255)
