@@ -67,7 +67,13 @@ enum {
     /* Use PIL's "over" arithmetic (movis/imgproc.py:197-213).  The reference takes this path iff
      * blending_mode is the NORMAL *enum* and matte_mode is NONE (imgproc.py:265-268); everything
      * else uses the numpy arithmetic of _overlay (imgproc.py:136-170). */
-    MVB_LAYER_PIL_OVER = 1
+    MVB_LAYER_PIL_OVER = 1,
+    /* mvb_layer only, optional: the caller knows that every pixel of `src` has alpha 255 (one reduction
+     * when the image is uploaded).  Pure work elimination: a NORMAL layer with opacity 1 and such a source
+     * replaces whatever lies below it wherever all of its taps fall inside the source (both "over"
+     * operators return the sample exactly there, imgproc.py:156-165 / 197-213), so the kernel does not
+     * walk the layers underneath in those tiles.  Never changes a pixel. */
+    MVB_LAYER_OPAQUE_SOURCE = 2
 };
 
 /* mvb_composite_stack flags */

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOVIS_B200_LIB") or os.path.join(_HERE, "csrc", "libmovis_b200.so")
 
 MVB_LAYER_PIL_OVER = 1
+MVB_LAYER_OPAQUE_SOURCE = 2
 MVB_STACK_KEEP_FRAME = 1
 MVB_BLUR_PLAIN, MVB_BLUR_GLOW = 0, 1
 

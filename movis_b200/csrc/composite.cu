@@ -34,8 +34,10 @@ constexpr int kTileW = 32;
 constexpr int kMaxLayers = 32;   // layers of one frame per launch (one per producer lane); longer stacks continue from the stored frame
 constexpr int kMaxMaps = 128;    // distinct TMA descriptors per launch: they travel as kernel parameters (16 KB)
 
-enum { kLayerPil = 1,    // PIL's "over" arithmetic (MVB_LAYER_PIL_OVER)
-       kLayerLut = 2 };  // set by k_stack_prep: the opacity table is not floor(a c) for any c; DevLayer::lut holds it
+enum { kLayerPil = 1,        // PIL's "over" arithmetic (MVB_LAYER_PIL_OVER)
+       kLayerLut = 2,        // set by k_stack_prep: the opacity table is not floor(a c) for any c; DevLayer::lut holds it
+       kLayerIntShift = 4,   // the inverse map is a translation by whole pixels: every sample is one texel
+       kLayerOccluder = 8 }; // NORMAL, opacity 1, source alpha 255 throughout: hides what is below wherever it covers
 
 constexpr int kPilOver = 18; // dispatch code of PIL's "over" next to the 18 numpy blend modes
 
@@ -178,6 +180,15 @@ static int fill_dev_layer(const mvb_layer& in, DevLayer& out)
     out.opacity = in.opacity;
     out.pil_a = (int32_t)std::nearbyint(in.opacity * 255.0);
     for (int i = 0; i < 6; i++) out.mf[i] = (float)out.m[i];
+    // cv2's tables for such a map are adelta = 1024 x, bdelta = 0, X0 = 1024 m2 + 16, Y0 = 1024 (y + m5) + 16,
+    // all exact: the fractions are 0 and the sample is the texel (x + m2, y + m5) itself
+    const double* m = out.m;
+    static const bool one_tap_off = std::getenv("MVB_DISABLE_ONE_TAP") != nullptr;   // diagnostics
+    if (!one_tap_off && m[0] == 1.0 && m[4] == 1.0 && m[1] == 0.0 && m[3] == 0.0 && m[2] == std::nearbyint(m[2]) &&
+        m[5] == std::nearbyint(m[5]) && std::fabs(m[2]) < 1e6 && std::fabs(m[5]) < 1e6)
+        out.flags |= kLayerIntShift;
+    if ((in.flags & MVB_LAYER_OPAQUE_SOURCE) && in.opacity >= 1.0 && (pil || in.blend_mode == MVB_BLEND_NORMAL))
+        out.flags |= kLayerOccluder;
     return 0;
 }
 

@@ -410,6 +410,9 @@ constexpr int kMaxStages = 8;   // shared-memory stages of TMA boxes in flight (
 //   kTileTmaLut / kTileTmaPartLut   the same for a layer whose opacity needs its table (kLayerLut)
 // Odd codes are the ones that use a TMA stage.
 enum { kTileEdge = 0, kTileTmaLut = 1, kTileInterior = 2, kTileTma = 3, kTileTmaPartLut = 5, kTileTmaPart = 7 };
+// With kTileTma only: the layer is shifted by whole pixels (kLayerIntShift), so a sample IS a texel: one tap
+// per pixel, no weights, no bilinear sums (cv2: fx = fy = 0, (1024 p + 512) >> 10 = p).
+constexpr int kInfoOneTap = 1 << 12;
 
 // cv2's bilinear weights of a sample at (sumx, sumy) (1/1024 px; 5 fractional bits are used), times 32:
 // wt = 32 (32 - fx)(32 - fy) | 32 fx (32 - fy) << 16,  wb = 32 (32 - fx) fy | 32 fx fy << 16  (imgwarp.cpp:
@@ -451,7 +454,7 @@ struct PixelCtx {
 // Layers without such a constant (opacity 0.7 is one) carry their 256-entry table in global memory and
 // travel through tile classes of their own (kTile*Lut), which look the value up; layers with a
 // constant pay nothing for that.
-template <bool OPAQUE, int QUADS, class Slot>
+template <bool OPAQUE, int QUADS, bool ONE_TAP, class Slot>
 __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* __restrict__ layers, const Slot& S,
                                            const int* layer_index, const PixelCtx& C,
                                            RowPairState (&d)[2 * QUADS], const float2* softg)
@@ -528,7 +531,16 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
     // other classes, which it orders with the common case last)
     uint32_t hot;
     asm("mov.b32 %0, %1;" : "=r"(hot) : "r"(info.x));
-    if ((hot & 0x700u) == (uint32_t)kTileTma << 8) {
+    if (ONE_TAP) {
+        // whole-pixel shift (kInfoOneTap): texel (x + m2, y + m5) of the staged box, rows one pitch apart
+        const uint32_t pitch = (uint32_t)info.x >> 16;
+        const int2 r0 = rowtab[0];
+        const uint32_t a0 = imad((uint32_t)((r0.y + col.y) >> 10), pitch, imad((uint32_t)((r0.x + col.x) >> 10), 4u, (uint32_t)info.w));
+        mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) t[q][0] = lds_u32(a0 + (uint32_t)q * pitch);
+        mbar_arrive_warp((uint32_t)info.y + 8 * kMaxStages);
+    } else if ((hot & 0x700u) == (uint32_t)kTileTma << 8) {
         staged(std::false_type{}, std::false_type{});
     } else if (cls == kTileTmaPart) {
         staged(std::true_type{}, std::false_type{});
@@ -582,25 +594,38 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
     const u64 oc2 = bc(oc), ok2 = bc(fmaf(oc, -kMagic, kMagic));
 #pragma unroll
     for (int p = 0; p < PAIRS; ++p) {
-        float v[2][4];
+        if (ONE_TAP) {   // the texel is the sample: bytes to biased floats
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int k = 2 * p + q;
-            const uint32_t t_rg = __byte_perm(t[k][0], t[k][1], 0x5140), t_ba = __byte_perm(t[k][0], t[k][1], 0x7362);
-            const uint32_t b_rg = __byte_perm(t[k][2], t[k][3], 0x5140), b_ba = __byte_perm(t[k][2], t[k][3], 0x7362);
-            v[q][0] = __uint_as_float(__dp2a_lo(wb[k], b_rg, __dp2a_lo(wt[k], t_rg, kTwo23Bits + 32u * 512u)));
-            v[q][1] = __uint_as_float(__dp2a_hi(wb[k], b_rg, __dp2a_hi(wt[k], t_rg, kTwo23Bits + 32u * 512u)));
-            v[q][2] = __uint_as_float(__dp2a_lo(wb[k], b_ba, __dp2a_lo(wt[k], t_ba, kTwo23Bits + 32u * 512u)));
-            v[q][3] = __uint_as_float(__dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, kTwo23Bits + 32u * 512u)));
+            for (int c = 0; c < 4; ++c)
+                s[p][c] = pk(__uint_as_float(__byte_perm(t[2 * p][0], kMagicBits, 0x7650 + c)),
+                             __uint_as_float(__byte_perm(t[2 * p + 1][0], kMagicBits, 0x7650 + c)));
+        } else {
+            float v[2][4];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int k = 2 * p + q;
+                const uint32_t t_rg = __byte_perm(t[k][0], t[k][1], 0x5140), t_ba = __byte_perm(t[k][0], t[k][1], 0x7362);
+                const uint32_t b_rg = __byte_perm(t[k][2], t[k][3], 0x5140), b_ba = __byte_perm(t[k][2], t[k][3], 0x7362);
+                v[q][0] = __uint_as_float(__dp2a_lo(wb[k], b_rg, __dp2a_lo(wt[k], t_rg, kTwo23Bits + 32u * 512u)));
+                v[q][1] = __uint_as_float(__dp2a_hi(wb[k], b_rg, __dp2a_hi(wt[k], t_rg, kTwo23Bits + 32u * 512u)));
+                v[q][2] = __uint_as_float(__dp2a_lo(wb[k], b_ba, __dp2a_lo(wt[k], t_ba, kTwo23Bits + 32u * 512u)));
+                v[q][3] = __uint_as_float(__dp2a_hi(wb[k], b_ba, __dp2a_hi(wt[k], t_ba, kTwo23Bits + 32u * 512u)));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)   // (2^23 + 32 (512 + sum)) / 32768 = 256 + (sum + 512) / 1024
+                s[p][c] = fma2_rm(pk(v[0][c], v[1][c]), bc(1.0f / 32768.0f), bc(kMagic - 256.0f));
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)   // (2^23 + 32 (512 + sum)) / 32768 = 256 + (sum + 512) / 1024
-            s[p][c] = fma2_rm(pk(v[0][c], v[1][c]), bc(1.0f / 32768.0f), bc(kMagic - 256.0f));
         // opacity-scaled alpha, plain (not biased): floor(a c) for the two rows in one fma.rm + one subtract
         fa[p] = sub2(fma2_rm(s[p][3], oc2, ok2), bc(kMagic));
     }
 
     // ---- blend, in the code specialised for this layer's mode ------------------------------------
+    if (ONE_TAP) {   // only NORMAL layers take this instantiation (numpy's or PIL's arithmetic): the kernel's
+                     // code must stay within reach of the instruction cache, a second copy of all 19 bodies does not
+        if ((info.x & 255) == 18) blend_rows<18, OPAQUE, PAIRS>(d, s, fa, softg, ok);
+        else blend_rows<0, OPAQUE, PAIRS>(d, s, fa, softg, ok);
+        return;
+    }
 #ifdef MVB_DIAG_MODE0      // (diagnostic build: every layer blends as NORMAL)
     switch (0) {
 #else

@@ -49,7 +49,7 @@ constexpr int kCullPitch = 21;                    // conflict-free by lane
 // Per layer of a unit.
 template <int ROWS>
 struct __align__(16) UnitSlot {
-    // x: mode (8 bits) | class (3) | phase parity of the stage (bit 11) | row pitch of the box << 16
+    // x: mode (8 bits) | class (3) | phase parity of the stage (bit 11) | kInfoOneTap (bit 12) | row pitch of the box << 16
     // y: address of the stage's "full" barrier ("empty" is 8 * kMaxStages bytes on)
     // z: the layer's opacity constant c (float bits)
     // w: address the stage would have at source pixel (0, 0): stage - origin
@@ -124,6 +124,7 @@ k_stack_prep(const PrepParams T)
         const FrameRec& F = T.frames[f];
         const int tx0 = (t % T.tiles_x) * kTileW, ty0 = (t / T.tiles_x) * T.tile_h;
         int cls = -1;
+        bool hides = false;   // the layer replaces everything below it in this tile
         int2 org = make_int2(0, 0);
         // (tiles outside the union of the layers' bboxes take the short way: background only)
         const bool covered = tx0 < F.ux1 && tx0 + kTileW > F.ux0 && ty0 < F.uy1 && ty0 + T.tile_h > F.uy0;
@@ -145,6 +146,11 @@ k_stack_prep(const PrepParams T)
                 const float yc = m3 * uc + m4 * vc + m5, ey = fabsf(m3) * hu + fabsf(m4) * hv;
                 const float xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
                 const bool full = u1 - u0 == kTileW - 1 && v1 - v0 == T.tile_h - 1;
+                // every tap of every pixel of the tile inside the source
+                const bool inside = xmin > 0.25f && xmax < src_w - 1.25f && ymin > 0.25f && ymax < src_h - 1.25f;
+                // (a tile the frame cuts short is as good as full for this purpose: the pixels that exist are covered)
+                hides = (L.flags & kLayerOccluder) && inside && u0 == max(tx0, 0) - bx && v0 == max(ty0, 0) - by &&
+                        u1 == min(tx0 + kTileW, T.W) - 1 - bx && v1 == min(ty0 + T.tile_h, T.H) - 1 - by;
                 // No tap inside the source: every sample is transparent.  A no-op for PIL's over and on an
                 // opaque frame; numpy's over still zeroes rgb where the frame's alpha is 0 (imgproc.py:164).
                 const bool nothing = xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f;
@@ -156,13 +162,23 @@ k_stack_prep(const PrepParams T)
                     if (box_w > 0 && (int)floorf(xmax) + 3 - fx0 <= box_w && (int)floorf(ymax) + 3 - fy0 <= box_h) {
                         cls = full ? kTileTma : kTileTmaPart;
                         org = make_int2(fx0, fy0);
-                    } else if (full && xmin > 0.25f && xmax < src_w - 1.25f && ymin > 0.25f && ymax < src_h - 1.25f) {
+                    } else if (full && inside) {
                         cls = kTileInterior;   // whole tile covered and every tap inside the source
                     }
                 }
             }
         }
-        const unsigned active = __ballot_sync(0xFFFFFFFFu, cls >= 0);
+        // An occluder (NORMAL, opacity 1, source alpha 255 everywhere) whose taps all lie inside its source
+        // samples alpha 255, and both "over" operators then return the sample whatever is underneath
+        // (numpy: (65025 T + 0) // 65025, alpha 65025 // 255; PIL: coef1 = 32640, coef2 = 0): the layers
+        // below the topmost one are dropped from the tile's list.  Bit-exact by construction.
+        unsigned active = __ballot_sync(0xFFFFFFFFu, cls >= 0);
+        const unsigned hiding = __ballot_sync(0xFFFFFFFFu, cls >= 0 && hides);
+        if (hiding) {
+            const int top = 31 - __clz((int)hiding);
+            active &= ~((1u << top) - 1u);
+            if (lane < top) cls = -1;
+        }
         int2* rec = T.tiles + ((size_t)f * (size_t)T.n_tiles + (size_t)t) * (size_t)T.tile_stride;
         if (lane == 0) rec[0] = make_int2(__popc(active) | (f << 8), tx0 | (ty0 << 16));   // count | frame << 8, tile origin
         if (active == 0u && !T.keep_frame && tx0 + lane < T.W) {
@@ -442,7 +458,8 @@ k_stack_frames(const __grid_constant__ FramesParams P)
             if (mine) {
                 const int pitch = C[6] * 4;   // box_w px
                 UnitSlot<ROWS>& S = U.slot[lane - base];
-                S.info = make_int4(C[14] | ((my_c & 7) << 8) | ((my_rd & 1) << 11) | (pitch << 16),
+                const int one_tap = (my_c == kTileTma && (C[15] & kLayerIntShift) && (C[14] == 0 || C[14] == kPilOver)) ? kInfoOneTap : 0;
+                S.info = make_int4(C[14] | ((my_c & 7) << 8) | ((my_rd & 1) << 11) | one_tap | (pitch << 16),
                                    (int)(bar_full + 8 * my_st),
                                    C[16],
                                    (int)(stage0 + my_st * P.stage_bytes - my_org.y * pitch - my_org.x * 4));
@@ -496,8 +513,14 @@ k_stack_frames(const __grid_constant__ FramesParams P)
                 }
             }
 #pragma unroll 1
-            for (int slot = 0; slot < n_here; ++slot)
-                walk_layer<OPAQUE, QUADS>(G, layers, U.slot[slot], &U.layer[slot], px, d, s_softg);
+            for (int slot = 0; slot < n_here; ++slot) {
+                // (whole-pixel shifts run their own instantiation, blend code included, so that the general
+                // walk is compiled exactly as if they did not exist)
+                if (__builtin_expect(!(U.slot[slot].info.x & kInfoOneTap), 1))
+                    walk_layer<OPAQUE, QUADS, false>(G, layers, U.slot[slot], &U.layer[slot], px, d, s_softg);
+                else
+                    walk_layer<OPAQUE, QUADS, true>(G, layers, U.slot[slot], &U.layer[slot], px, d, s_softg);
+            }
             mbar_arrive_warp(unit_empty + 8 * (u & (kWsUnits - 1)));   // this warp no longer reads the unit
             if ((hdr.z & 512) && x_ok) {   // last unit of the tile: one coalesced 128-byte store per warp row
 #pragma unroll

@@ -123,7 +123,10 @@ def fill_descriptors(out: np.ndarray, image, plan: AffinePlan, opacity: np.ndarr
     out["blend_mode"] = blending_mode.value
     # Composition always composites with MatteMode.NONE, so the enum NORMAL selects PIL's
     # arithmetic and every other mode numpy's (imgproc.py:265-273).
-    out["flags"] = _native.MVB_LAYER_PIL_OVER if blending_mode == BlendingMode.NORMAL else 0
+    flags = _native.MVB_LAYER_PIL_OVER if blending_mode == BlendingMode.NORMAL else 0
+    if getattr(image, "mvb_opaque", False):   # device.upload_source: alpha is 255 throughout
+        flags |= _native.MVB_LAYER_OPAQUE_SOURCE
+    out["flags"] = flags
     out["opacity"] = opacity
 
 

@@ -15,7 +15,7 @@ from typing import Sequence
 import numpy as np
 from PIL import Image as PILImage
 
-from ..device import to_device
+from ..device import to_device, upload_source  # noqa: F401
 from ..util import to_rgb
 from .mixin import TimelineMixin
 
@@ -96,7 +96,7 @@ class Image:
         if not (0 <= time < self.duration):
             return None
         if self._device_image is None:
-            self._device_image = to_device(self._read_image())
+            self._device_image = upload_source(self._read_image())
         return self._device_image
 
     def __getstate__(self):  # device tensors stay behind when a scene is shipped to a worker
@@ -156,7 +156,7 @@ class ImageSequence(TimelineMixin):
         if i < 0:
             return None
         if self._device_images[i] is None:
-            self._device_images[i] = to_device(self._host_image(i))
+            self._device_images[i] = upload_source(self._host_image(i))
         return self._device_images[i]
 
     def __getstate__(self):

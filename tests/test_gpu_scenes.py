@@ -154,6 +154,60 @@ def test_crop_and_matte_layers_in_a_composition_match_reference_golden(golden):
         assert np.array_equal(comp2(1.3), g["frame_div2_L2"])
 
 
+def _occlusion_scene(mv, size=(300, 200)):
+    """Whole-pixel shifts (the one-tap path), opaque NORMAL layers at opacity 1 that hide what is below them
+    (dropped from the tile lists), and the near misses of both: fractional shifts, opacity 0.999, a
+    non-NORMAL mode, an opaque layer that is rotated (hides only the tiles it covers completely)."""
+    from movis_b200.scenes import synthetic_rgba
+    W, H = size
+    comp = mv.layer.Composition(size=size, duration=2.0)
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8000, 150, 260, "random", rim=5)), name="under", position=(140.0, 90.0),
+                   rotation=20.0, blending_mode="screen")
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8001, H, W, "opaque")), name="cover")                  # hides "under" everywhere
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8002, 120, 170, "random")), name="shifted", position=(100.0, 70.0),
+                   opacity=0.7, blending_mode="overlay")                                                 # whole-pixel shift, odd size / 2 = .5 offsets
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8003, 120, 170, "random")), name="shifted_int", position=(185.0, 110.0),
+                   origin_point="top_left", blending_mode="multiply")
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8004, 96, 128, "opaque")), name="patch", position=(64.0, 48.0))      # occluder over 64 x 96 .. inside the frame
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8005, 96, 128, "opaque")), name="patch_frac", position=(200.25, 60.5))
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8006, 160, 220, "opaque")), name="spin", position=(150.0, 100.0), rotation=33.0)
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8007, 80, 80, "opaque")), name="almost", position=(250.0, 150.0), opacity=0.999)
+    comp.add_layer(mv.layer.Image(synthetic_rgba(8008, 80, 80, "opaque")), name="lighten", position=(40.0, 160.0), blending_mode="lighten")
+    item = comp.add_layer(mv.layer.Image(synthetic_rgba(8009, 64, 64, "opaque")), name="mover", position=(20.0, 20.0))
+    item.position.enable_motion().extend([0.0, 2.0], [(20.0, 20.0), (280.0, 180.0)])                  # whole and fractional positions, leaves the frame
+    return comp
+
+
+def test_whole_pixel_shifts_and_hidden_layers_vs_oracle():
+    mv, _ = _mv()
+    comp = _occlusion_scene(mv)
+    for t in (0.0, 0.5, 1.0, 1.37, 1.99):
+        for bg in ((0, 0, 0, 0), (9, 8, 7, 255)):
+            _assert_matches_oracle(comp, t, bg)
+    _assert_matches_oracle(comp, 1.0, (9, 8, 7, 255), level=2)
+    big = _occlusion_scene(mv, size=(1000, 700))          # several whole tiles under the cover
+    _assert_matches_oracle(big, 0.25, (0, 0, 0, 255))
+    _assert_matches_oracle(big, 0.25, (0, 0, 0, 0))
+
+
+def test_opaque_source_flag_never_changes_a_pixel():
+    """MVB_LAYER_OPAQUE_SOURCE is work elimination only: the same stack with and without the flag."""
+    import torch
+    from movis_b200 import _native
+    from movis_b200.render import launch_plan, plan_range
+    mv, _ = _mv()
+    comp = _occlusion_scene(mv, size=(640, 360))
+    times = np.array([0.0, 0.7, 1.5])
+    plan = plan_range(comp, times)
+    assert (plan.descriptors["flags"] & _native.MVB_LAYER_OPAQUE_SOURCE).any()
+    out = [torch.zeros((3, 360, 640, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    launch_plan(plan, out[0], (1, 2, 3, 255))
+    plan.descriptors["flags"] &= ~_native.MVB_LAYER_OPAQUE_SOURCE
+    launch_plan(plan, out[1], (1, 2, 3, 255))
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], out[1])
+
+
 def test_batched_frames_equal_per_frame_renders():
     import torch
     from movis_b200 import scenes
