@@ -186,13 +186,29 @@ def pinned_sources():
     return out
 
 
-def timeline(world: int, rank: int) -> np.ndarray:
+def timeline(world: int, rank: int, weights=None) -> np.ndarray:
     """This rank's share of the job: ONE timeline of 150 * world frames (the 5 s scene at 30 * world
-    fps), contiguous index range render.shard_range(150 world, rank, world)."""
+    fps), contiguous index range render.shard_range(150 world, rank, world[, weights])."""
     from movis_b200.render import shard_range
     total = FRAMES_PER_STEP * world
-    mine = shard_range(total, rank, world)
+    mine = shard_range(total, rank, world, weights)
     return np.asarray(mine, dtype=np.float64) / (FPS * world)
+
+
+def delivery_weights(world: int):
+    """Per-rank device -> host copy rates with every rank copying at once (GB/s), the weights of the
+    delivered-frame legs: on the boxes of this pool half of the GPUs get half the PCIe rate of the others
+    when all eight copy (profiles/r02_pcie_concurrent.json), and equal shares would wait for them."""
+    if world == 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    from movis_b200.render import d2h_rate
+    barrier(world)
+    mine = torch.tensor([d2h_rate() / 1e9], dtype=torch.float64, device="cuda")
+    rates = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(rates, mine)
+    return [round(float(r.item()), 2) for r in rates]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -382,12 +398,15 @@ def run_product(args) -> dict:
     d2h = FRAMES_PER_STEP * H * W * 4
     e2e_steps = max(1, min(args.steps, 3))
 
+    weights = delivery_weights(world)
+    times_e2e = timeline(world, rank, weights)     # this rank's share of the SAME 150 * world frames
+
     def e2e_step():
         comp.cache.clear()
         for item in comp.layers:
             item.layer._device_image = None          # forces the H2D upload of every source
         n = 0
-        for _frame in stream_frames(comp, times, bg_color=BG, copy=False):
+        for _frame in stream_frames(comp, times_e2e, bg_color=BG, copy=False):
             n += 1
         return n
 
@@ -395,13 +414,14 @@ def run_product(args) -> dict:
     barrier(world)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        assert e2e_step() == FRAMES_PER_STEP
+        assert e2e_step() == len(times_e2e)
     barrier(world)
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0, world)
     e2e = {"value": world * e2e_steps * FRAMES_PER_STEP / e2e_elapsed, "unit": UNIT,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
            "d2h_GBps": world * e2e_steps * d2h / e2e_elapsed / 1e9,
-           "api": "movis_b200.render.stream_frames (Composition._write_video loop)"}
+           "api": "movis_b200.render.stream_frames (Composition._write_video loop)",
+           "shard_weights_GBps": weights}
 
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -418,7 +438,7 @@ def run_product(args) -> dict:
         twins.clear()
         comp = None
         torch.cuda.empty_cache()
-        result["s5"] = run_s5(world, rank)
+        result["s5"] = run_s5(world, rank, weights)
         if rank == 0 and world == 1:
             result["configs"] = other_configs(peak)
             result["cpu_baseline"] = cpu_baseline()
@@ -428,7 +448,7 @@ def run_product(args) -> dict:
     return result if rank == 0 else {}
 
 
-def run_s5(world: int, rank: int) -> dict:
+def run_s5(world: int, rank: int, weights=None) -> dict:
     import torch
     import movis_b200 as mv
     from movis_b200 import scenes
@@ -451,10 +471,11 @@ def run_s5(world: int, rank: int) -> dict:
     barrier(world)
     device_s = max_over_ranks(ev0.elapsed_time(ev1) / 1e3, world)
     del out
+    times_d = np.asarray(shard_range(N, rank, world, weights), dtype=np.float64) / FPS   # delivered leg: weighted ranges
     barrier(world)
     t0 = time.perf_counter()
     n = 0
-    for _ in stream_frames(comp, times, bg_color=BG, copy=False):
+    for _ in stream_frames(comp, times_d, bg_color=BG, copy=False):
         n += 1
     barrier(world)
     delivered_s = max_over_ranks(time.perf_counter() - t0, world)

@@ -20,6 +20,19 @@ def test_shard_range_partitions():
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
+def test_weighted_shard_range_partitions():
+    """Uneven contiguous ranges (ranks that deliver frames faster own more of the timeline)."""
+    for n in (0, 1, 7, 150, 1800):
+        for w in ([1.0], [1.0, 1.0], [9.0, 9.0, 9.0, 8.0, 18.0, 18.0, 18.0, 18.0], [0.2, 5.0, 1.0]):
+            g = len(w)
+            parts = [shard_range(n, r, g, w) for r in range(g)]
+            assert [i for p in parts for i in p] == list(range(n))
+            for r in range(g):   # within one frame of the exact share
+                assert abs(len(parts[r]) - n * w[r] / sum(w)) <= 1.0 + 1e-9
+    assert [len(shard_range(150, r, 2, [1.0, 1.0])) for r in range(2)] == [75, 75]
+    assert [len(shard_range(1200, r, 8, [9, 9, 9, 9, 18, 18, 18, 18])) for r in range(8)] == [100] * 4 + [200] * 4
+
+
 def _free_port() -> int:
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
