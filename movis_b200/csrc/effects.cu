@@ -104,12 +104,12 @@ __global__ void __launch_bounds__(256) k_blur_v_rgba(const __grid_constant__ Blu
 // ---- tiled RGBA blur (k <= kTiledMaxK, every weight <= 255) ---------------------------------------
 // Same arithmetic as k_blur_h_rgba / k_blur_v_rgba; what changes is the data movement.
 //   H: a CTA stages one row segment (1024 outputs + k + 3 taps, padding rule applied once) in shared
-//      memory, transposed so that "thread t, tap j" is conflict-free; every thread produces 4
-//      adjacent outputs from a sliding window, two channels per IMAD (16-bit lanes: a Q8 weighted
-//      sum of bytes stays below 65 536), weights broadcast from shared memory.
+//      memory as four channel PLANES (4 x 4 byte transposes), so a word holds one channel of four adjacent
+//      pixels; every thread produces 4 adjacent outputs, four taps of a channel per IDP.4A (u8 x u8,
+//      32-bit accumulate; a Q8 weighted sum of bytes stays below 65 536), weights broadcast from shared memory.
 //   V: every thread produces 4 vertically adjacent outputs of one column, so each intermediate
-//      row is loaded once per 4 outputs (coalesced 8-byte loads); one IDP.2A per channel and tap
-//      (16-bit value x 8-bit weight, 32-bit accumulate).
+//      row is loaded once per 4 outputs (coalesced 8-byte loads); one IDP.2A per channel and PAIR of taps
+//      (two 16-bit values x two 8-bit weights, 32-bit accumulate).
 constexpr int kTiledMaxK = 255;
 constexpr int kBlurHOut = 1024;   // outputs per CTA of the H pass (4 per thread)
 
@@ -117,78 +117,106 @@ __global__ void __launch_bounds__(256) k_blur_h_rgba_tiled(const __grid_constant
 {
     extern __shared__ uint32_t s_dyn[];
     const int k = P.k, r = k >> 1, W2 = P.w + 2 * k;
-    const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);     // staged pixels (taps of the last output, rounded up)
-    const int Q = n_in >> 2;
-    uint32_t* s_px = s_dyn;                                // pixel i at (i & 3) * Q + (i >> 2)
-    uint32_t* s_w = s_dyn + n_in;                          // weight of tap jj at s_w[jj + 3]; zeros around
+    const int G = kBlurHOut / 4 + (k + 2) / 4 + 1;         // groups of 4 staged pixels (taps of the last output included)
+    uint32_t* s_pl = s_dyn;                                // plane c, group g at s_pl[c * G + g]: channel c of pixels 4 g .. 4 g + 3
+    uint4* s_w = reinterpret_cast<uint4*>(s_dyn + 4 * G);  // s_w[q] = for m = 0 .. 3 the bytes w(4 q - m), .., w(4 q + 3 - m)
     const int y = blockIdx.y, X0 = blockIdx.x * kBlurHOut;
     const int t = threadIdx.x;
     const uint32_t* row = reinterpret_cast<const uint32_t*>(P.src + (int64_t)y * P.sstride);
-    for (int i = t; i < n_in; i += 256) {
-        const int sx = X0 + i - r - k;                     // source x of staged pixel i (blur.py:39-40 padding)
-        uint32_t p = __ldg(row + min(max(sx, 0), P.w - 1));
-        if ((unsigned)sx >= (unsigned)P.w) p &= 0x00FFFFFFu;   // rgb edge-replicated, alpha zero-padded
-        s_px[(i & 3) * Q + (i >> 2)] = p;
+    for (int g = t; g < G; g += 256) {
+        uint32_t p[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int sx = X0 + 4 * g + b - r - k;         // source x of staged pixel 4 g + b (blur.py:39-40 padding)
+            p[b] = __ldg(row + min(max(sx, 0), P.w - 1));
+            if ((unsigned)sx >= (unsigned)P.w) p[b] &= 0x00FFFFFFu;   // rgb edge-replicated, alpha zero-padded
+        }
+        // 4 x 4 byte transpose: pixels -> channel planes
+        const uint32_t t0 = __byte_perm(p[0], p[1], 0x5140), t1 = __byte_perm(p[2], p[3], 0x5140);
+        const uint32_t u0 = __byte_perm(p[0], p[1], 0x7362), u1 = __byte_perm(p[2], p[3], 0x7362);
+        s_pl[g] = __byte_perm(t0, t1, 0x5410);
+        s_pl[G + g] = __byte_perm(t0, t1, 0x7632);
+        s_pl[2 * G + g] = __byte_perm(u0, u1, 0x5410);
+        s_pl[3 * G + g] = __byte_perm(u0, u1, 0x7632);
     }
-    for (int j = t; j < k + 12; j += 256) s_w[j] = (j >= 3 && j < k + 3) ? P.wt[j - 3] : 0u;
+    const int Q = (k + 2) / 4 + 1;                         // groups that hold taps of a thread's 4 outputs
+    for (int i = t; i < 4 * Q; i += 256) {
+        const int q = i >> 2, m = i & 3;
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int tap = 4 * q + b - m;
+            if (tap >= 0 && tap < k) w |= (uint32_t)P.wt[tap] << (8 * b);
+        }
+        reinterpret_cast<uint32_t*>(s_w)[i] = w;
+    }
     __syncthreads();
-    uint32_t rb[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0};
-    for (int j4 = 0; j4 * 4 < k + 3; ++j4) {
-        const uint4 wa = *reinterpret_cast<const uint4*>(s_w + 4 * j4);        // taps 4 j4 - 3 .. 4 j4
-        const uint4 wb = *reinterpret_cast<const uint4*>(s_w + 4 * j4 + 4);    // taps 4 j4 + 1 .. 4 j4 + 4
-        const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    // Output X0 + 4 t + m takes staged pixel 4 (t + q) + b as tap 4 q + b - m: one IDP.4A per channel, group
+    // and output (four taps each), the four weight alignments of a group in one broadcast 128-bit load.
+    uint32_t acc[4][4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const uint32_t p = s_px[jj * Q + t + j4];      // staged pixel 4 t + 4 j4 + jj
-            const uint32_t prb = p & 0x00FF00FFu, pga = (p >> 8) & 0x00FF00FFu;
+    for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0u;
+    for (int q = 0; q < Q; ++q) {
+        const uint4 w = s_w[q];
+        const uint32_t wm[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {                  // output 4 t + m takes it as tap 4 j4 + jj - m
-                rb[m] += w[jj - m + 3] * prb;
-                ga[m] += w[jj - m + 3] * pga;
-            }
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t px = s_pl[c * G + t + q];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m][c] = __dp4a(px, wm[m], acc[m][c]);
         }
     }
     uint2* out = reinterpret_cast<uint2*>(P.mid) + (int64_t)y * W2;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const int X = X0 + 4 * t + m;
-        if (X < W2) out[X] = make_uint2((rb[m] & 0xFFFFu) | (ga[m] << 16), (rb[m] >> 16) | (ga[m] & 0xFFFF0000u));
+        if (X < W2) out[X] = make_uint2(acc[m][0] | (acc[m][1] << 16), acc[m][2] | (acc[m][3] << 16));
     }
 }
 
+constexpr int kBlurVOut = 8;   // vertically adjacent outputs per thread of the V pass
+
 __global__ void __launch_bounds__(256) k_blur_v_rgba_tiled(const __grid_constant__ BlurParams P)
 {
-    __shared__ uint2 s_w[kTiledMaxK + 9];                  // tap jj at s_w[jj + 3]: (w, w << 8) for the two dp2a halves
+    __shared__ uint32_t s_w[kTiledMaxK + 2 * kBlurVOut + 4];   // s_w[t + kBlurVOut - 1] = w(t) | w(t + 1) << 8, w = 0 outside [0, k)
     const int k = P.k, r = k >> 1;
     const int W2 = P.w + 2 * k, H2 = P.h + 2 * k;
-    for (int j = threadIdx.x; j < k + 8; j += 256) {
-        const uint32_t w = (j >= 3 && j < k + 3) ? P.wt[j - 3] : 0u;
-        s_w[j] = make_uint2(w, w << 8);
+    for (int j = threadIdx.x; j < k + 2 * kBlurVOut + 4; j += 256) {
+        const int t = j - (kBlurVOut - 1);
+        const uint32_t w0 = (t >= 0 && t < k) ? P.wt[t] : 0u, w1 = (t + 1 >= 0 && t + 1 < k) ? P.wt[t + 1] : 0u;
+        s_w[j] = w0 | (w1 << 8);
     }
     __syncthreads();
     const int X = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int Yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 4;
+    const int Yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kBlurVOut;
     if (X >= W2 || Yb >= H2) return;
     const uint2* mid = reinterpret_cast<const uint2*>(P.mid) + X;
-    uint32_t acc[4][4];
+    uint32_t acc[kBlurVOut][4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 32768u;   // rounding of (V + 32768) >> 16
+    for (int m = 0; m < kBlurVOut; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 32768u;   // rounding of (V + 32768) >> 16
     const int y0 = Yb - r - k;
-    for (int j = 0; j < k + 3; ++j) {                      // intermediate row y0 + j is tap j - m of output Yb + m
-        const int sy = y0 + j;
-        uint2 v = __ldg(mid + (int64_t)min(max(sy, 0), P.h - 1) * W2);
-        if ((unsigned)sy >= (unsigned)P.h) v.y &= 0xFFFFu; // alpha zero-padded
+    // Two intermediate rows per step: the same channel of rows j and j + 1 side by side (one PRMT) is the
+    // 16-bit pair of one IDP.2A, whose byte pair is (w(j - m), w(j + 1 - m)) for output Yb + m: two taps
+    // per instruction.  Row j is tap j - m of output m; rows past the last tap meet zero weights.
+    for (int j = 0; j < k + kBlurVOut - 1; j += 2) {
+        const int sy0 = y0 + j, sy1 = sy0 + 1;
+        uint2 v0 = __ldg(mid + (int64_t)min(max(sy0, 0), P.h - 1) * W2);
+        uint2 v1 = __ldg(mid + (int64_t)min(max(sy1, 0), P.h - 1) * W2);
+        if ((unsigned)sy0 >= (unsigned)P.h) v0.y &= 0xFFFFu;   // alpha zero-padded
+        if ((unsigned)sy1 >= (unsigned)P.h) v1.y &= 0xFFFFu;
+        const uint32_t rr = __byte_perm(v0.x, v1.x, 0x5410), gg = __byte_perm(v0.x, v1.x, 0x7632);
+        const uint32_t bb = __byte_perm(v0.y, v1.y, 0x5410), aa = __byte_perm(v0.y, v1.y, 0x7632);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const uint2 w = s_w[j - m + 3];
-            acc[m][0] = __dp2a_lo(v.x, w.x, acc[m][0]);
-            acc[m][1] = __dp2a_lo(v.x, w.y, acc[m][1]);
-            acc[m][2] = __dp2a_lo(v.y, w.x, acc[m][2]);
-            acc[m][3] = __dp2a_lo(v.y, w.y, acc[m][3]);
+        for (int m = 0; m < kBlurVOut; ++m) {
+            const uint32_t w = s_w[j - m + kBlurVOut - 1];
+            acc[m][0] = __dp2a_lo(rr, w, acc[m][0]);
+            acc[m][1] = __dp2a_lo(gg, w, acc[m][1]);
+            acc[m][2] = __dp2a_lo(bb, w, acc[m][2]);
+            acc[m][3] = __dp2a_lo(aa, w, acc[m][3]);
         }
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < kBlurVOut; ++m) {
         const int Y = Yb + m;
         if (Y >= H2) break;
         Rgba s{acc[m][0] >> 16, acc[m][1] >> 16, acc[m][2] >> 16, acc[m][3] >> 16};
@@ -645,10 +673,10 @@ extern "C" int mvb_effect_blur_rgba8(const void* src, int32_t w, int32_t h, int6
     bool tiled = k <= kTiledMaxK;
     for (int j = 0; j < k; j++) tiled = tiled && weights[j] <= 255;   // IDP.2A takes 8-bit weights
     if (tiled) {
-        const int n_in = kBlurHOut + ((k + 3 + 3) & ~3);
-        k_blur_h_rgba_tiled<<<dim3((W2 + kBlurHOut - 1) / kBlurHOut, h), 256, (n_in + k + 12) * 4, st>>>(P);
+        const int groups = kBlurHOut / 4 + (k + 2) / 4 + 1, wq = (k + 2) / 4 + 1;
+        k_blur_h_rgba_tiled<<<dim3((W2 + kBlurHOut - 1) / kBlurHOut, h), 256, (4 * groups + 4 * wq) * 4, st>>>(P);
         count_launches(1);
-        k_blur_v_rgba_tiled<<<dim3((W2 + 31) / 32, (H2 + 31) / 32), 256, 0, st>>>(P);
+        k_blur_v_rgba_tiled<<<dim3((W2 + 31) / 32, (H2 + 8 * kBlurVOut - 1) / (8 * kBlurVOut)), 256, 0, st>>>(P);
         count_launches(1);
     } else {
         k_blur_h_rgba<<<dim3((W2 + 31) / 32, (h + 7) / 8), 256, 0, st>>>(P);
