@@ -460,12 +460,13 @@ def run_s5(world: int, rank: int, weights=None) -> dict:
     times = np.asarray(mine, dtype=np.float64) / FPS
     for _ in stream_frames(comp, times[:16], bg_color=BG, copy=False):   # warm-up: uploads, effect caches
         pass
-    out = torch.empty((60,) + comp.frame_shape() + (4,), dtype=torch.uint8, device="cuda")
+    CALL = 240   # frames per render_frames call (8 GB of frames resident; the call plans 240 frames at once)
+    out = torch.empty((CALL,) + comp.frame_shape() + (4,), dtype=torch.uint8, device="cuda")
     barrier(world)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(0, len(times), 60):
-        chunk = times[i:i + 60]
+    for i in range(0, len(times), CALL):
+        chunk = times[i:i + CALL]
         render_frames(comp, chunk, bg_color=BG, out=out[:len(chunk)])
     ev1.record()
     barrier(world)

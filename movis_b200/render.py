@@ -91,6 +91,11 @@ class RangePlan:
     def n_frames(self) -> int:
         return len(self.offsets) - 1
 
+    def slice(self, a: int, b: int) -> "RangePlan":
+        """Frames [a, b) of this plan (views of the same tables)."""
+        lo, hi = int(self.offsets[a]), int(self.offsets[b])
+        return RangePlan(self.descriptors[lo:hi], (self.offsets[a:b + 1] - self.offsets[a]).astype(np.int32), self.keepalive)
+
 
 def _static_content(item: LayerItem) -> bool:
     """True when the post-effect image of ``item`` cannot change while it is visible, so one
@@ -168,13 +173,17 @@ def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
                                 samples.rotation[js_arr], samples.opacity[js_arr], samples.origin_point,
                                 samples.blending_mode)
             plan = plan_affine(sub, size, L)
-            for local, j in enumerate(js):
-                if not plan.valid[local]:
-                    continue
-                one = type(plan)(plan.matrix[local:local + 1], plan.bbox[local:local + 1], plan.valid[local:local + 1])
-                fill_descriptors(rows[j:j + 1], images[j], one, sub.opacity[local:local + 1], samples.blending_mode)
-                ok[j] = True
-                keep.append(images[j])
+            # one vectorised fill per size; what differs from frame to frame besides the transform is the
+            # image (pointer, row stride, whether its alpha is known to be 255 throughout)
+            group = np.zeros(len(js), dtype=_native.LAYER_DTYPE)
+            fill_descriptors(group, images[js[0]], plan, sub.opacity, samples.blending_mode)
+            group["src"] = [images[j].data_ptr() for j in js]
+            group["src_stride"] = [images[j].stride(0) for j in js]
+            opaque = np.fromiter((bool(getattr(images[j], "mvb_opaque", False)) for j in js), dtype=bool, count=len(js))
+            group["flags"] = (group["flags"] & ~_native.MVB_LAYER_OPAQUE_SOURCE) | np.where(opaque, _native.MVB_LAYER_OPAQUE_SOURCE, 0)
+            rows[js_arr] = group
+            ok[js_arr] = plan.valid
+            keep.extend(images[j] for j in js)
         per_layer.append((idx[ok], rows[ok]))
 
     counts = np.zeros(n, dtype=np.int64)
@@ -253,29 +262,83 @@ def stream_frames(comp: Composition, times: Sequence[float], bg_color=(0, 0, 0, 
     if len(times) == 0:
         return
     batch = max(1, min(batch, len(times)))
-    dev = [torch.empty((batch, H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
-    host = [torch.empty((batch, H, W, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    copy_stream = torch.cuda.Stream()
-    render_done = [torch.cuda.Event() for _ in range(2)]
-    copy_done = [torch.cuda.Event() for _ in range(2)]
+    ring = _staging_ring(batch, H, W)
+    try:
+        yield from _stream_with(ring, comp, times, bg_color, batch, copy)
+    finally:
+        ring["busy"] = False
+
+
+_RINGS: dict = {}
+
+
+def _staging_ring(batch: int, H: int, W: int) -> dict:
+    """Two device batches, two pinned host batches, a copy stream and their events, kept per (device,
+    batch, frame size) between calls: pinning half a gigabyte takes ~0.1-1 s, far more than rendering
+    the frames that go through it.  A ring in use by a live generator is not shared (a second concurrent
+    stream of the same shape gets a private one)."""
+    key = (torch.cuda.current_device(), batch, H, W)
+    ring = _RINGS.get(key)
+    if ring is not None and not ring["busy"]:
+        for e in ring["copy_done"]:
+            e.synchronize()   # an abandoned generator may have left a copy in flight
+        ring["busy"] = True
+        return ring
+    fresh = {
+        "dev": [torch.empty((batch, H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)],
+        "host": [torch.empty((batch, H, W, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)],
+        "copy_stream": torch.cuda.Stream(),
+        "render_done": [torch.cuda.Event() for _ in range(2)],
+        "copy_done": [torch.cuda.Event() for _ in range(2)],
+        "busy": True,
+    }
+    if ring is None:
+        if len(_RINGS) >= 4:   # a handful of shapes at most (full size and draft levels)
+            _RINGS.pop(next(iter(_RINGS)))
+        _RINGS[key] = fresh
+    return fresh
+
+
+def _stream_with(ring: dict, comp: Composition, times: np.ndarray, bg_color, batch: int, copy: bool) -> Iterator[np.ndarray]:
+    dev, host, copy_stream = ring["dev"], ring["host"], ring["copy_stream"]
+    render_done, copy_done = ring["render_done"], ring["copy_done"]
     main = torch.cuda.current_stream()
 
-    def submit(slot: int, chunk: np.ndarray) -> None:
+    # Keyframes are evaluated for plan_chunk(comp) frames at a time (a handful of numpy calls per layer
+    # whatever the count), independently of the copy batch: a batch takes its slice of the current plan.
+    # The first plan is short, so the first frames leave early and the long plans that follow are made
+    # while copies are in flight.
+    step = max(batch, plan_chunk(comp) // batch * batch)
+    bounds = [0, min(2 * batch, len(times))]
+    while bounds[-1] < len(times):
+        bounds.append(min(bounds[-1] + step, len(times)))
+    state = {"chunk": -1, "plan": None}
+
+    def plan_for(first: int, n: int) -> RangePlan:
+        c = int(np.searchsorted(bounds, first, side="right")) - 1
+        if state["chunk"] != c:
+            state["plan"] = plan_range(comp, times[bounds[c]:bounds[c + 1]])
+            state["chunk"] = c
+        return state["plan"].slice(first - bounds[c], first - bounds[c] + n)
+
+    def submit(slot: int, first: int, n: int) -> None:
         main.wait_event(copy_done[slot])  # the previous copy out of dev[slot] must be finished
-        render_frames(comp, chunk, bg_color, out=dev[slot][: len(chunk)])
+        launch_plan(plan_for(first, n), dev[slot][:n], bg_color)
         render_done[slot].record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(render_done[slot])
-            host[slot][: len(chunk)].copy_(dev[slot][: len(chunk)], non_blocking=True)
+            host[slot][:n].copy_(dev[slot][:n], non_blocking=True)
             copy_done[slot].record(copy_stream)
 
-    chunks = [times[i:i + batch] for i in range(0, len(times), batch)]
-    submit(0, chunks[0])
-    for i, chunk in enumerate(chunks):
+    assert np.all((times >= 0.0) & (times < comp.duration)), "all times must lie in [0, duration)"
+    starts = list(range(0, len(times), batch))
+    counts = [min(batch, len(times) - a) for a in starts]
+    submit(0, starts[0], counts[0])
+    for i, n in enumerate(counts):
         slot = i & 1
-        if i + 1 < len(chunks):
-            submit(slot ^ 1, chunks[i + 1])
+        if i + 1 < len(starts):
+            submit(slot ^ 1, starts[i + 1], counts[i + 1])
         copy_done[slot].synchronize()
         frames = host[slot].numpy()
-        for j in range(len(chunk)):
+        for j in range(n):
             yield frames[j].copy() if copy else frames[j]
