@@ -23,6 +23,7 @@ job, all GPUs).
             (profiles/roofline_traffic.json; `traffic_source` says so: it is not measured by this run).
   configs   device frames/s and roofline fraction of the other BASELINE.json configs (S1, S2d, S3, S4 at
             draft levels 1/2/4, S5), each from a few hundred ms of rendering
+  operators_4k  the stand-alone effect kernels at 4K through the C ABI (us per call, GB/s, roofline fraction)
   s5        BASELINE.json configs[4]: the 1800-frame 4K timeline, frame-sharded over the ranks (STRONG
             scaling: total work fixed): device and delivered frames/s of the whole job
   cpu_baseline  the reference's algorithm on the host cores (rank 0, N = 1): the real reference when it
@@ -31,8 +32,11 @@ job, all GPUs).
 Multi-GPU: launched with torchrun, one rank per GPU.  The job is ONE fixed timeline of 150 * N frames
 (the 5 s scene sampled at 30 * N fps); rank r renders the contiguous index range
 render.shard_range(150 N, r, N) of it, so ranks render DIFFERENT frames and per-GPU work is fixed
-(weak scaling).  Ranks exchange no pixels -- torch.distributed is used only for the barrier and the
-max-over-ranks reduction of the elapsed time.
+(weak scaling).  Ranks exchange no pixels -- torch.distributed is used only for the barrier, the
+max-over-ranks reduction of the elapsed time and the all-gather of eight numbers below.
+The delivered-frame legs (e2e, s5 delivered) split the same timeline in proportion to each rank's
+device -> host copy rate measured with all ranks copying at once (render.d2h_rate, e2e.shard_weights_GBps):
+on this pool's 8-GPU boxes half of the GPUs get half the PCIe rate of the others under load.
 """
 from __future__ import annotations
 
@@ -278,8 +282,67 @@ def other_configs(peak: float) -> dict:
     comp = scenes.build_s4(mv, ChromaKey)
     for level in (1, 2, 4):
         record(f"S4 L={level} (configs[3]: chroma-keyed 4K sequence over a 4.2K background)", time_scene(comp, full[:48], level=level),
-               s4_bytes_per_frame(level), 48, "the chroma key runs as its own pass per distinct sequence frame (8 of them, cached)")
+               s4_bytes_per_frame(level), 48, "the chroma key runs as its own pass once per distinct sequence frame (8 of them; cached through ChromaKey.get_key)")
     del comp
+    torch.cuda.empty_cache()
+    return out
+
+
+def operator_timings(peak: float) -> dict:
+    """The stand-alone effect operators at 4K through the C ABI with preallocated buffers (CUDA events over
+    40 back-to-back calls on four alternating inputs): microseconds per call and algorithmic GB/s
+    (input + output once; blur counts as one stage)."""
+    import torch
+    from movis_b200 import _native
+    L = _native.lib()
+    H, W, reps = 2160, 3840, 40
+    g = torch.Generator(device="cuda").manual_seed(0)
+    src = [torch.randint(0, 256, (H, W, 4), dtype=torch.uint8, device="cuda", generator=g) for _ in range(4)]
+    for t in src:
+        t[: H // 2, :, 0] = 0
+        t[: H // 2, :, 1] = 255
+        t[: H // 2, :, 2] = 0
+    dst = torch.empty((H + 200, W + 200, 4), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+
+    def timed(name, fn, nbytes):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        out[name] = {"us": round(us, 1), "GBps": round(nbytes / us / 1e3, 1), "roofline_frac": round(nbytes / us / 1e3 / peak, 3)}
+
+    lo, hi = np.array([50, 178, 178], np.uint8), np.array([70, 255, 255], np.uint8)
+    timed("ChromaKey()", lambda i: _native.check(L.mvb_effect_chroma_key_rgba8(
+        src[i & 3].data_ptr(), W, H, W * 4, dst.data_ptr(), dst.stride(0), lo.ctypes.data, hi.ctypes.data, stream)), 2 * H * W * 4)
+    col = np.array([255, 0, 0], np.uint8)
+    timed("FillColor", lambda i: _native.check(L.mvb_effect_fill_color_rgba8(
+        src[i & 3].data_ptr(), W, H, W * 4, dst.data_ptr(), dst.stride(0), col.ctypes.data, stream)), 2 * H * W * 4)
+    x = np.arange(256, dtype=np.uint8)
+    lut = np.ascontiguousarray((x.astype(np.int32) * 3 // 4).astype(np.uint8))
+    timed("HSLShift", lambda i: _native.check(L.mvb_effect_hsl_shift_rgba8(
+        src[i & 3].data_ptr(), W, H, W * 4, dst.data_ptr(), dst.stride(0), lut.ctypes.data, lut.ctypes.data, lut.ctypes.data,
+        stream)), 2 * H * W * 4)
+    for radius in (3.0, 10.0):
+        k = _native.blur_ksize(radius)
+        wts = _native.gaussian_weights_q8(radius, k)
+        scratch = torch.empty(L.mvb_effect_blur_scratch_bytes(W, H, k, 4), dtype=torch.uint8, device="cuda")
+        glow = np.clip(1.3 * x.astype(np.float32), 0, 255).astype(np.uint8)
+        nbytes = H * W * 4 + (H + 2 * k) * (W + 2 * k) * 4
+        timed(f"GaussianBlur({radius:g})", lambda i: _native.check(L.mvb_effect_blur_rgba8(
+            src[i & 3].data_ptr(), W, H, W * 4, dst.data_ptr(), dst.stride(0), k, wts.ctypes.data, _native.MVB_BLUR_PLAIN,
+            None, scratch.data_ptr(), stream)), nbytes)
+        timed(f"Glow({radius:g}, 1.3)", lambda i: _native.check(L.mvb_effect_blur_rgba8(
+            src[i & 3].data_ptr(), W, H, W * 4, dst.data_ptr(), dst.stride(0), k, wts.ctypes.data, _native.MVB_BLUR_GLOW,
+            glow.ctypes.data, scratch.data_ptr(), stream)), nbytes)
+    del src, dst
     torch.cuda.empty_cache()
     return out
 
@@ -441,6 +504,7 @@ def run_product(args) -> dict:
         result["s5"] = run_s5(world, rank, weights)
         if rank == 0 and world == 1:
             result["configs"] = other_configs(peak)
+            result["operators_4k"] = operator_timings(peak)
             result["cpu_baseline"] = cpu_baseline()
     if world > 1:
         import torch.distributed as dist
