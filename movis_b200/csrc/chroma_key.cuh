@@ -15,8 +15,8 @@
 //     0, 1, .., 5 diff, -diff, .., -1, (0): it climbs from 0 to 150, the wrap lifts the negative
 //     numerators to [150, 180), and the last few of them round to 0 again.  So "lo_h <= h <= hi_h" is an
 //     arc of that cycle: "(n - n0(diff)) mod (6 diff + 1) <= span(diff)"      -> hq[diff]
-// The per-texel test is then max/min, the hue numerator, two table reads and two unsigned compares
-// (the tables are 1 KB each; build_chroma_tables checks the arc structure instead of assuming it).
+// The per-texel test is then max/min, the hue numerator, two table reads and three packed range tests
+// (1 KB + 2 KB of tables; build_chroma_tables checks the arc structure instead of assuming it).
 #pragma once
 
 #include <cstdint>
@@ -24,12 +24,18 @@
 
 namespace mvb {
 
+// Table entries are "packed range tests": for a range [a, b] of a quantity x (all below 2^15) the word
+// E = b * 65536 - a gives  Z = x * 0xFFFF0001 + E = (x - a) + (b - x) * 65536,  whose bits 15 and 31 are
+// both clear exactly when a <= x <= b (a negative low half borrows from the high half, but then bit 15 is
+// set already): one IMAD and one LOP3 per test instead of unpacking two bounds.  An empty range is
+// a = 0x7FFF, b = 0.
 struct ChromaTables {
-    uint32_t sv[256];   // by v:    d0 | (d1 - d0) << 16; an empty range is 0x7FFF | 0 << 16
-    uint32_t hq[256];   // by diff: (n0 + 256) | span << 16, empty likewise
+    uint32_t sv[256];   // by v:    diff in [d0, d1]
+    uint2 hq[256];      // by diff: n + 256 in [a1, b1] or in [a2, b2] (the arc of the cycle, cut where it wraps)
 };
 
-constexpr uint32_t kChromaEmpty = 0x7FFFu;
+constexpr uint32_t kChromaEmpty = 0u * 65536u - 0x7FFFu;
+__host__ __device__ inline uint32_t chroma_range(int a, int b) { return (uint32_t)b * 65536u - (uint32_t)a; }
 
 // Host: false when the in-range set is not of the form above (cannot happen for cv2's tables; the
 // caller then keeps the full conversion).
@@ -58,7 +64,7 @@ inline bool build_chroma_tables(const uint8_t lo[3], const uint8_t hi[3], Chroma
                 }
             }
         }
-        T.sv[v] = d0 < 0 ? kChromaEmpty : (uint32_t)d0 | ((uint32_t)(d1 - d0) << 16);
+        T.sv[v] = d0 < 0 ? kChromaEmpty : chroma_range(d0, d1);
     }
     for (int diff = 0; diff < 256; diff++) {
         const int M = 6 * diff + 1;                              // numerators -diff .. 5 diff, cyclically
@@ -72,34 +78,49 @@ inline bool build_chroma_tables(const uint8_t lo[3], const uint8_t hi[3], Chroma
             in[j] = h >= lo[0] && h <= hi[0];
             count += in[j];
         }
-        if (count == 0) { T.hq[diff] = kChromaEmpty; continue; }
-        if (count == M) { T.hq[diff] = (uint32_t)(256 - diff) | ((uint32_t)(M - 1) << 16); continue; }
+        T.hq[diff] = make_uint2(kChromaEmpty, kChromaEmpty);
+        if (count == 0) continue;
         int starts = 0, first = 0;
         for (int j = 0; j < M; j++)
             if (in[j] && !in[(j + M - 1) % M]) { ++starts; first = j; }
+        if (count == M) { starts = 1; first = 0; }
         if (starts != 1) return false;
-        T.hq[diff] = (uint32_t)(first - diff + 256) | ((uint32_t)(count - 1) << 16);
+        // the arc [first, first + count) of the cycle of length M, in j = n + diff; as n + 256: j + 256 - diff
+        const int off = 256 - diff, last = first + count - 1;
+        if (last < M) {
+            T.hq[diff].x = chroma_range(first + off, last + off);
+        } else {
+            T.hq[diff].x = chroma_range(first + off, M - 1 + off);
+            T.hq[diff].y = chroma_range(0 + off, last - M + off);
+        }
     }
     return true;
 }
 
 #ifdef __CUDACC__
 // One texel: true when cv2.inRange(cvtColor(rgb -> hsv), lower, upper) holds (the pixel is keyed out).
-__device__ __forceinline__ bool chroma_in_range(uint32_t p, const uint32_t* __restrict__ sv, const uint32_t* __restrict__ hq)
+// Bytes are picked and differenced by IDP.4A (the FMA pipe is idle here, the ALU pipe is the busy one).
+__device__ __forceinline__ int dp4a_us(uint32_t a, int32_t b_signed_bytes, int c)
 {
-    const int r = (int)__byte_perm(p, 0, 0x4440), g = (int)__byte_perm(p, 0, 0x4441), b = (int)__byte_perm(p, 0, 0x4442);
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_signed_bytes), "r"(c));
+    return d;
+}
+__device__ __forceinline__ bool chroma_in_range(uint32_t p, const uint32_t* __restrict__ sv, const uint2* __restrict__ hq)
+{
+    const int r = (int)__dp4a(p, 0x00000001u, 0u), g = (int)__dp4a(p, 0x00000100u, 0u), b = (int)__dp4a(p, 0x00010000u, 0u);
     const int v = max(max(r, g), b), diff = v - min(min(r, g), b);
-    // the three numerators are two operations each: computing all of them and selecting is cheaper than
-    // the divergent branches the compiler makes of the conditional expression
-    const int n_r = g - b + 256, n_g = b - r + 2 * diff + 256, n_b = r - g + 4 * diff + 256;
+    // hue numerators + 256: g - b, b - r + 2 diff, r - g + 4 diff (signed byte weights 0x00FF0100 = (0, +1, -1, 0) ...)
+    const int n_r = dp4a_us(p, 0x00FF0100, 256), n_g = dp4a_us(p, 0x000100FF, 2 * diff + 256), n_b = dp4a_us(p, 0x0000FF01, 4 * diff + 256);
     int n;
     asm("{\n.reg .pred pr, pg;\nsetp.eq.s32 pr, %1, %2;\nsetp.eq.s32 pg, %1, %3;\n"
         "selp.s32 %0, %5, %6, pg;\nselp.s32 %0, %4, %0, pr;\n}"
         : "=r"(n) : "r"(v), "r"(r), "r"(g), "r"(n_r), "r"(n_g), "r"(n_b));
-    const uint32_t e = sv[v], q = hq[diff];
-    int t = n - (int)(q & 0xFFFFu);
-    if (t < 0) t += 6 * diff + 1;
-    return (uint32_t)(diff - (int)(e & 0xFFFFu)) <= (e >> 16) && (uint32_t)t <= (q >> 16);
+    const uint32_t e = sv[v];
+    const uint2 q = hq[diff];
+    const uint32_t zs = (uint32_t)diff * 0xFFFF0001u + e;
+    const uint32_t z1 = (uint32_t)n * 0xFFFF0001u + q.x, z2 = (uint32_t)n * 0xFFFF0001u + q.y;
+    return !(zs & 0x80008000u) && (!(z1 & 0x80008000u) || !(z2 & 0x80008000u));
 }
 #endif
 

@@ -494,19 +494,20 @@ struct ChromaParams {
     int32_t w, h, sstride, dstride;
     uint32_t per_row, total;      // vectors per row, vectors in the image
     uint32_t rcp_mul, rcp_shift;  // i / per_row == umulhi(i, rcp_mul) >> rcp_shift for i < total
-    ChromaTables tab;
+    const ChromaTables* tab;      // in global memory (chroma_tables_on_device): 3 KB, read once per CTA, coalesced
 };
 
 template <int VEC>
 __global__ void __launch_bounds__(256) k_chroma_key(const __grid_constant__ ChromaParams P)
 {
-    __shared__ uint32_t s_sv[256], s_hq[256];
-    s_sv[threadIdx.x] = P.tab.sv[threadIdx.x];
-    s_hq[threadIdx.x] = P.tab.hq[threadIdx.x];
+    __shared__ uint32_t s_sv[256];
+    __shared__ uint2 s_hq[256];
+    s_sv[threadIdx.x] = __ldg(&P.tab->sv[threadIdx.x]);
+    s_hq[threadIdx.x] = __ldg(&P.tab->hq[threadIdx.x]);
     __syncthreads();
     typedef typename std::conditional<VEC == 4, uint4, uint32_t>::type Vec;
     auto locate = [&](uint32_t i, int64_t& so, int64_t& dof) {
-        const uint32_t y = __umulhi(i, P.rcp_mul) >> P.rcp_shift, x = i - y * P.per_row;
+        const uint32_t y = P.rcp_mul ? __umulhi(i, P.rcp_mul) >> P.rcp_shift : i, x = i - y * P.per_row;
         so = (int64_t)y * P.sstride + (int64_t)x * (4 * VEC);
         dof = (int64_t)y * P.dstride + (int64_t)x * (4 * VEC);
     };
@@ -763,21 +764,49 @@ static int launch_pointwise(PointParams& P, const void* src, int w, int h, int64
     return check_launch(what);
 }
 
+// The bounds tables of a key, built once and kept in device memory for the life of the process (an effect
+// instance keeps its key; a program uses a handful).  Passing the 3 KB as a kernel parameter made every CTA
+// copy them out of the constant bank with a different address per lane, i.e. serially.  *out stays null
+// when build_chroma_tables refuses the key.
+static int chroma_tables_on_device(const uint8_t lo[3], const uint8_t hi[3], cudaStream_t stream, const ChromaTables** out)
+{
+    static std::mutex mu;
+    static std::vector<std::pair<uint64_t, const ChromaTables*>> known;   // (device << 48 | lo << 24 | hi) -> tables
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t key = ((uint64_t)dev << 48) | ((uint64_t)lo[0] << 40) | ((uint64_t)lo[1] << 32) | ((uint64_t)lo[2] << 24) |
+                         ((uint64_t)hi[0] << 16) | ((uint64_t)hi[1] << 8) | (uint64_t)hi[2];
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& e : known)
+        if (e.first == key) { *out = e.second; return MVB_OK; }
+    static ChromaTables host;
+    const ChromaTables* devp = nullptr;
+    if (build_chroma_tables(lo, hi, host)) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, sizeof host) != cudaSuccess) { cudaGetLastError(); return set_error(MVB_ERR_CUDA, "no device memory for the chroma key tables"); }
+        // visible to every stream before the pointer is published: copy on the caller's stream, then wait for it
+        cudaError_t e = cudaMemcpyAsync(p, &host, sizeof host, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { cudaFree(p); return set_error(MVB_ERR_CUDA, cudaGetErrorString(e)); }
+        devp = static_cast<const ChromaTables*>(p);
+    }
+    if (known.size() >= 256) {   // (unbounded key churn: start over; the old tables may still be in use, so they are kept)
+        known.clear();
+    }
+    known.emplace_back(key, devp);
+    *out = devp;
+    return MVB_OK;
+}
+
 extern "C" int mvb_effect_chroma_key_rgba8(const void* src, int32_t w, int32_t h, int64_t sstride, void* dst,
                                            int64_t dstride, const uint8_t lo[3], const uint8_t hi[3],
                                            mvb_stream_t stream)
 {
     if (!lo || !hi) return set_error(MVB_ERR_INVALID_ARG, "bounds are null");
-    // the bounds tables of the last key used by this thread (an effect instance keeps its key for life)
-    static thread_local ChromaParams C;
-    static thread_local uint8_t c_lo[3], c_hi[3];
-    static thread_local int c_state = 0;   // 0: nothing cached, 1: tables valid, -1: this key needs the full conversion
-    if (c_state == 0 || std::memcmp(c_lo, lo, 3) || std::memcmp(c_hi, hi, 3)) {
-        c_state = build_chroma_tables(lo, hi, C.tab) ? 1 : -1;
-        std::memcpy(c_lo, lo, 3);
-        std::memcpy(c_hi, hi, 3);
-    }
-    if (c_state < 0) {
+    if (int rc = require_device()) return rc;
+    const ChromaTables* tab = nullptr;
+    if (int rc = chroma_tables_on_device(lo, hi, (cudaStream_t)stream, &tab)) return rc;
+    if (!tab) {   // (this key's in-range set is not an arc: keep the full conversion)
         PointParams P;
         std::memset(&P, 0, sizeof P);
         P.op = 0;
@@ -785,7 +814,8 @@ extern "C" int mvb_effect_chroma_key_rgba8(const void* src, int32_t w, int32_t h
         std::memcpy(P.hi, hi, 3);
         return launch_pointwise(P, src, w, h, sstride, dst, dstride, stream, "mvb_effect_chroma_key_rgba8");
     }
-    if (int rc = require_device()) return rc;
+    ChromaParams C;
+    C.tab = tab;
     if (int rc = check_rgba(src, w, h, sstride, "src")) return rc;
     if (int rc = check_rgba(dst, w, h, dstride, "dst")) return rc;
     C.src = static_cast<const uint8_t*>(src);
@@ -797,12 +827,13 @@ extern "C" int mvb_effect_chroma_key_rgba8(const void* src, int32_t w, int32_t h
     if (total >= (1ull << 31)) return set_error(MVB_ERR_UNSUPPORTED, "image too large");
     C.per_row = (uint32_t)per_row;
     C.total = (uint32_t)total;
-    // floor(i / d) = (i * m) >> (32 + s) with m = ceil(2^(32+s) / d), exact for i < 2^31 when s = ceil(log2 d)
-    uint32_t sh = 0;
-    while ((1ull << sh) < per_row) ++sh;
-    C.rcp_shift = sh;
-    C.rcp_mul = (uint32_t)((((1ull << (32 + sh)) + per_row - 1) / per_row) & 0xFFFFFFFFull);
-    if (per_row == 1) { C.rcp_mul = 0xFFFFFFFFu; C.rcp_shift = 0; }
+    // floor(i / d) = umulhi(i, m) >> (l - 1) with l = ceil(log2 d), m = ceil(2^(31 + l) / d) <= 2^32 - 1 for d > 1:
+    // m d - 2^(31 + l) < d <= 2^l, so the error term i (m d - 2^(31 + l)) stays below 2^(31 + l) for i < 2^31.
+    // d == 1 is flagged by m == 0.
+    uint32_t l = 0;
+    while ((1ull << l) < per_row) ++l;
+    C.rcp_mul = per_row == 1 ? 0u : (uint32_t)(((1ull << (31 + l)) + per_row - 1) / per_row);
+    C.rcp_shift = per_row == 1 ? 0u : l - 1;
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const unsigned grid = (unsigned)std::min<uint64_t>((total + 511) / 512, (uint64_t)n_sm * 6);

@@ -254,6 +254,16 @@ def test_pointwise_effects_vs_oracle_ragged_widths(dev):
         img[:3, :, :3] = (0, 255, 0)
         assert np.array_equal(mv.effect.HSLShift(77.0, -0.2, 0.3)(img, 0.0), O.effect_hsl_shift(img, 77.0, -0.2, 0.3)), w
         assert np.array_equal(ChromaKey()(img, 0.0), O.effect_chroma_key(img)), w
+    # strided inputs (crops of a wider device image: ops.crop hands those out), vector and scalar widths
+    import torch
+    from movis_b200.device import to_device
+    wide = rng.integers(0, 256, (37, 300, 4), dtype=np.uint8)
+    wide[5:20, 40:200, :3] = (0, 255, 0)
+    dev = to_device(wide)
+    for x0, ww in ((0, 300), (4, 256), (8, 100), (3, 97), (12, 4), (1, 1), (16, 960 // 4)):
+        view = dev[2:35, x0:x0 + ww]
+        got = ChromaKey().apply_device(view, 0.0).cpu().numpy()
+        assert np.array_equal(got, O.effect_chroma_key(np.ascontiguousarray(wide[2:35, x0:x0 + ww]))), (x0, ww)
     full = rng.integers(0, 256, (2160, 3840, 4), dtype=np.uint8)  # config-4 sized green screen
     full[:1080, :, :3] = (0, 255, 0)
     got = ChromaKey()(full, 0.0)
