@@ -178,7 +178,7 @@ constexpr int kBlurVOut = 8;   // vertically adjacent outputs per thread of the 
 
 __global__ void __launch_bounds__(256) k_blur_v_rgba_tiled(const __grid_constant__ BlurParams P)
 {
-    __shared__ uint32_t s_w[kTiledMaxK + 2 * kBlurVOut + 4];   // s_w[t + kBlurVOut - 1] = w(t) | w(t + 1) << 8, w = 0 outside [0, k)
+    __shared__ __align__(16) uint32_t s_w[kTiledMaxK + 2 * kBlurVOut + 4];   // s_w[t + kBlurVOut - 1] = w(t) | w(t + 1) << 8, w = 0 outside [0, k)
     const int k = P.k, r = k >> 1;
     const int W2 = P.w + 2 * k, H2 = P.h + 2 * k;
     for (int j = threadIdx.x; j < k + 2 * kBlurVOut + 4; j += 256) {
@@ -206,9 +206,17 @@ __global__ void __launch_bounds__(256) k_blur_v_rgba_tiled(const __grid_constant
         if ((unsigned)sy1 >= (unsigned)P.h) v1.y &= 0xFFFFu;
         const uint32_t rr = __byte_perm(v0.x, v1.x, 0x5410), gg = __byte_perm(v0.x, v1.x, 0x7632);
         const uint32_t bb = __byte_perm(v0.y, v1.y, 0x5410), aa = __byte_perm(v0.y, v1.y, 0x7632);
+        // the weights of the 8 outputs are 8 consecutive words (j is even: four aligned 64-bit loads, broadcast)
+        uint32_t wv[kBlurVOut];
+#pragma unroll
+        for (int q = 0; q < kBlurVOut / 2; ++q) {
+            const uint2 t = *reinterpret_cast<const uint2*>(&s_w[j + 2 * q]);
+            wv[2 * q] = t.x;
+            wv[2 * q + 1] = t.y;
+        }
 #pragma unroll
         for (int m = 0; m < kBlurVOut; ++m) {
-            const uint32_t w = s_w[j - m + kBlurVOut - 1];
+            const uint32_t w = wv[kBlurVOut - 1 - m];
             acc[m][0] = __dp2a_lo(rr, w, acc[m][0]);
             acc[m][1] = __dp2a_lo(gg, w, acc[m][1]);
             acc[m][2] = __dp2a_lo(bb, w, acc[m][2]);
