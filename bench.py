@@ -190,13 +190,17 @@ def pinned_sources():
     return out
 
 
-def timeline(world: int, rank: int, weights=None) -> np.ndarray:
+def timeline(world: int, rank: int, weights=None, comp=None) -> np.ndarray:
     """This rank's share of the job: ONE timeline of 150 * world frames (the 5 s scene at 30 * world
-    fps), contiguous index range render.shard_range(150 world, rank, world[, weights])."""
-    from movis_b200.render import shard_range
+    fps), contiguous index range render.shard_range(150 world, rank, world[, weights][, costs]).  With
+    `comp` the cuts balance the frames' estimated cost (render.frame_costs: the layers of S2 grow by 44 %
+    over the timeline) instead of their count; every rank computes the same cuts from the same scene."""
+    from movis_b200.render import frame_costs, shard_range
     total = FRAMES_PER_STEP * world
-    mine = shard_range(total, rank, world, weights)
-    return np.asarray(mine, dtype=np.float64) / (FPS * world)
+    all_times = np.arange(total, dtype=np.float64) / (FPS * world)
+    costs = frame_costs(comp, all_times) if (comp is not None and world > 1) else None
+    mine = shard_range(total, rank, world, weights, costs)
+    return all_times[mine.start:mine.stop]
 
 
 def delivery_weights(world: int):
@@ -361,9 +365,9 @@ def run_product(args) -> dict:
     lib = _native.lib()
     sources = pinned_sources()
     comp = scenes.build_s2(mv, div=1, variant=0, sources=sources)
-    times = timeline(world, rank)
+    times = timeline(world, rank, comp=comp)
     H, W = comp.frame_shape()
-    frames = torch.empty((FRAMES_PER_STEP, H, W, 4), dtype=torch.uint8, device="cuda")
+    frames = torch.empty((len(times), H, W, 4), dtype=torch.uint8, device="cuda")
 
     # Two device copies of the sources, alternated frame by frame through render_frames' plan hook, so no
     # frame finds the previous frame's texels in L2 (inputs per frame 133 MB + 33 MB out > 126 MB L2 anyway).
@@ -407,7 +411,8 @@ def run_product(args) -> dict:
 
     # --- roofline of the fused kernel: launches only, plans prebuilt, CUDA events on the launch stream
     from movis_b200.render import PLAN_CHUNK
-    plans = [alternate(plan_range(comp, times[i:i + PLAN_CHUNK]), i) for i in range(0, FRAMES_PER_STEP, PLAN_CHUNK)]
+    n_mine = len(times)   # this rank's frames per step (150 at N = 1; cost-balanced around 150 otherwise)
+    plans = [alternate(plan_range(comp, times[i:i + PLAN_CHUNK]), i) for i in range(0, n_mine, PLAN_CHUNK)]
 
     def launch_all():
         for k, p in enumerate(plans):
@@ -424,7 +429,7 @@ def run_product(args) -> dict:
     k1.record()
     torch.cuda.synchronize()
     runs = (int(lib.mvb_kernel_launches()) - n0) // 2 // reps      # each run = k_stack_prep + k_stack_frames
-    frame_s = k0.elapsed_time(k1) / 1e3 / (reps * FRAMES_PER_STEP)
+    frame_s = k0.elapsed_time(k1) / 1e3 / (reps * n_mine)
     # the same frames one per call (mvb_composite_stack: a run of one frame each), for comparison with
     # per-frame launch schemes
     bg_arr = np.asarray(BG, dtype=np.uint8)
@@ -446,7 +451,7 @@ def run_product(args) -> dict:
     b_frame = scenes.s2_bytes_per_frame(1)
     peak, peak_src = measured_hbm_peak()
     achieved = b_frame / frame_s / 1e9
-    frames_per_launch = FRAMES_PER_STEP / max(runs, 1)
+    frames_per_launch = n_mine / max(runs, 1)
     traffic_frame, traffic_src = recorded_traffic_per_frame()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None if traffic_frame is None else traffic_frame * frames_per_launch,

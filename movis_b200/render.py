@@ -43,23 +43,66 @@ def plan_chunk(comp: Composition) -> int:
     return int(min(PLAN_CHUNK, max(16, NESTED_BATCH_BYTES // worst)))
 
 
-def shard_range(n_frames: int, rank: int, world_size: int, weights: Sequence[float] | None = None) -> range:
+def shard_range(n_frames: int, rank: int, world_size: int, weights: Sequence[float] | None = None,
+                costs: Sequence[float] | None = None) -> range:
     """Contiguous frame indices owned by ``rank``: [floor(r N / G), floor((r + 1) N / G)).
 
     With ``weights`` (one positive number per rank, the same list on every rank) the cut points follow the
     cumulative weights instead, so a rank that delivers frames faster owns a longer -- still contiguous --
     range.  On the 8-GPU boxes measured here the device -> host copy rate differs 2 : 1 between GPUs when
     all of them copy at once (profiles/r02_pcie_concurrent.json), and the delivered frame rate is the
-    slowest rank's; ``d2h_rate`` measures the weights."""
+    slowest rank's; ``d2h_rate`` measures the weights.
+
+    With ``costs`` (one non-negative number per frame, e.g. ``frame_costs``) the cuts balance the summed
+    cost instead of the frame count: frames late in S2's timeline carry 40 % more layer pixels than early
+    ones, and with equal counts every rank waits for the one that owns the end of the timeline."""
     assert 0 <= rank < world_size
-    if weights is None:
+    if weights is None and costs is None:
         return range((rank * n_frames) // world_size, ((rank + 1) * n_frames) // world_size)
-    w = np.asarray(weights, dtype=np.float64)
+    w = np.ones(world_size) if weights is None else np.asarray(weights, dtype=np.float64)
     assert w.shape == (world_size,) and np.all(w > 0), "one positive weight per rank"
-    cuts = np.concatenate([[0.0], np.cumsum(w)]) / w.sum() * n_frames
-    cuts = np.floor(cuts + 1e-9).astype(np.int64)
+    share = np.concatenate([[0.0], np.cumsum(w)]) / w.sum()          # cumulative share of the work per rank
+    if costs is None:
+        cuts = np.floor(share * n_frames + 1e-9).astype(np.int64)
+    else:
+        c = np.asarray(costs, dtype=np.float64)
+        assert c.shape == (n_frames,) and np.all(c >= 0)
+        acc = np.concatenate([[0.0], np.cumsum(c)])
+        total = acc[-1] if acc[-1] > 0 else 1.0
+        # first frame index whose cumulative cost reaches the rank's share (monotone, so ranges stay contiguous)
+        cuts = np.searchsorted(acc / total, share - 1e-12, side="left").astype(np.int64)
+        cuts[0] = 0
     cuts[-1] = n_frames
+    cuts = np.maximum.accumulate(cuts)
     return range(int(cuts[rank]), int(cuts[rank + 1]))
+
+
+def frame_costs(comp: Composition, times: Sequence[float]) -> np.ndarray:
+    """Relative render cost of every frame of ``times``: frame pixels + the bbox pixels of every layer that
+    is composited (what the fused kernel walks).  Host only, a few numpy calls per layer for the whole
+    range; every rank computes the same numbers from the same scene, so ``shard_range(…, costs=…)`` needs no
+    communication."""
+    times = np.asarray(times, dtype=np.float64)
+    H, W = comp.frame_shape()
+    L = comp.preview_level
+    cost = np.full(len(times), float(H * W))
+    for item in comp.layers:
+        if not item.visible:
+            continue
+        layer_times = times - item.offset
+        idx = np.nonzero(~((layer_times < item.start_time) | (item.end_time <= layer_times)))[0]
+        if len(idx) == 0:
+            continue
+        size = getattr(item.layer, "size", None)
+        if size is None and isinstance(item.layer, Composition):
+            size = item.layer.size
+        if size is None:
+            continue   # (unknown source size: left out of the estimate)
+        plan = plan_affine(item.transform.sample(layer_times[idx]), (int(size[0]) // L or 1, int(size[1]) // L or 1)
+                           if isinstance(item.layer, Composition) else (int(size[0]), int(size[1])), L)
+        area = np.where(plan.valid, plan.bbox[:, 2].astype(np.float64) * plan.bbox[:, 3], 0.0)
+        cost[idx] += np.minimum(area, 4.0 * H * W)
+    return cost
 
 
 def d2h_rate(nbytes: int = 256 << 20, repeats: int = 3) -> float:

@@ -33,6 +33,29 @@ def test_weighted_shard_range_partitions():
     assert [len(shard_range(1200, r, 8, [9, 9, 9, 9, 18, 18, 18, 18])) for r in range(8)] == [100] * 4 + [200] * 4
 
 
+def test_cost_balanced_shard_range():
+    """Contiguous ranges that balance a per-frame cost (and combine with per-rank weights)."""
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 150, 1200):
+        for g in (1, 2, 4, 8):
+            cost = rng.uniform(0.5, 2.0, n) * np.linspace(1.0, 1.5, n)
+            parts = [shard_range(n, r, g, costs=cost) for r in range(g)]
+            assert [i for p in parts for i in p] == list(range(n))
+            if n >= 150:
+                sums = [cost[p.start:p.stop].sum() for p in parts]
+                assert max(sums) - min(sums) <= 2 * cost.max() + 1e-9
+    n, cost = 1200, np.linspace(1.0, 1.4, 1200)
+    parts = [shard_range(n, r, 8, costs=cost) for r in range(8)]
+    assert len(parts[0]) > len(parts[-1])                      # cheap frames: longer range
+    both = [shard_range(n, r, 2, weights=[1.0, 3.0], costs=np.ones(n)) for r in range(2)]
+    assert [len(p) for p in both] == [300, 900]
+    import movis_b200 as mv
+    from movis_b200 import scenes
+    from movis_b200.render import frame_costs
+    c = frame_costs(scenes.build_s2(mv, div=24), np.arange(0, 5, 1 / 30))
+    assert c.shape == (150,) and c[-1] > c[0] > 0              # the layers grow over the timeline
+
+
 def _free_port() -> int:
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
