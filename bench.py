@@ -178,6 +178,18 @@ def max_over_ranks(seconds: float, world: int) -> float:
     return float(t.item())
 
 
+def gather_floats(values, world: int):
+    """Every rank's list of floats, as a list of lists (diagnostics: per-rank step times and frame counts)."""
+    import torch
+    if world == 1:
+        return [list(values)]
+    import torch.distributed as dist
+    mine = torch.tensor(values, dtype=torch.float64, device="cuda")
+    out = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [[round(float(v), 3) for v in t.tolist()] for t in out]
+
+
 def pinned_sources():
     """The 16 S2 source images as numpy arrays backed by pinned host memory."""
     import torch
@@ -399,12 +411,15 @@ def run_product(args) -> dict:
     barrier(world)
     launches0 = int(lib.mvb_kernel_launches())
     ev0.record()
+    host0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+    host_s = time.perf_counter() - host0
     ev1.record()
     barrier(world)
     launches = int(lib.mvb_kernel_launches()) - launches0
     elapsed = max_over_ranks(ev0.elapsed_time(ev1) / 1e3, world)
+    per_rank = gather_floats([ev0.elapsed_time(ev1) / args.steps, host_s / args.steps * 1e3, float(len(times))], world)
     clocks = sampler.stop() if rank == 0 else {}
     total_frames = world * args.steps * FRAMES_PER_STEP
     value = total_frames / elapsed
@@ -498,6 +513,8 @@ def run_product(args) -> dict:
         "config": bench_config(world),
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "host_binding": getattr(dist_setup, "binding", None),
+        "per_rank": {"device_ms_per_step": [r[0] for r in per_rank], "host_ms_per_step": [r[1] for r in per_rank],
+                     "frames_per_step": [int(r[2]) for r in per_rank]},
     }
 
     if not args.quick:

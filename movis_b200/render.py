@@ -78,8 +78,8 @@ def shard_range(n_frames: int, rank: int, world_size: int, weights: Sequence[flo
 
 
 def frame_costs(comp: Composition, times: Sequence[float]) -> np.ndarray:
-    """Relative render cost of every frame of ``times``: frame pixels + the bbox pixels of every layer that
-    is composited (what the fused kernel walks).  Host only, a few numpy calls per layer for the whole
+    """Relative render cost of every frame of ``times``: frame pixels + the pixels every composited layer
+    covers (what the fused kernel walks).  Host only, a few numpy calls per layer for the whole
     range; every rank computes the same numbers from the same scene, so ``shard_range(…, costs=…)`` needs no
     communication."""
     times = np.asarray(times, dtype=np.float64)
@@ -100,8 +100,13 @@ def frame_costs(comp: Composition, times: Sequence[float]) -> np.ndarray:
             continue   # (unknown source size: left out of the estimate)
         plan = plan_affine(item.transform.sample(layer_times[idx]), (int(size[0]) // L or 1, int(size[1]) // L or 1)
                            if isinstance(item.layer, Composition) else (int(size[0]), int(size[1])), L)
-        area = np.where(plan.valid, plan.bbox[:, 2].astype(np.float64) * plan.bbox[:, 3], 0.0)
-        cost[idx] += np.minimum(area, 4.0 * H * W)
+        # pixels the layer covers: source area times |det| of the forward map, never more than its bbox
+        # (the bbox of a rotated layer is mostly empty tiles, which the kernel culls)
+        m = plan.matrix.reshape(-1, 6)
+        w_src, h_src = (int(size[0]) // L or 1, int(size[1]) // L or 1) if isinstance(item.layer, Composition) else (int(size[0]), int(size[1]))
+        covered = np.abs(m[:, 0] * m[:, 4] - m[:, 1] * m[:, 3]) * float(w_src * h_src)
+        bbox = plan.bbox[:, 2].astype(np.float64) * plan.bbox[:, 3]
+        cost[idx] += np.where(plan.valid, np.minimum(np.minimum(covered, bbox), 4.0 * H * W), 0.0)
     return cost
 
 
