@@ -42,21 +42,27 @@ def _layer_matrices(anchor: np.ndarray, position: np.ndarray, scale: np.ndarray,
                     origin: Direction, size: tuple[int, int]) -> np.ndarray:
     """Stacked ``T1 @ SR @ T2`` (N, 3, 3).  numpy's stacked matmul performs the same per-slice
     products as the reference's 3x3 ``@`` (tests/test_host_engine.py pins that bit for bit)."""
+    cx, cy = Direction.to_vector(origin, (float(size[0]), float(size[1])))
+    return _layer_matrices_xy(anchor, position, scale, rotation, cx, cy)
+
+
+def _layer_matrices_xy(anchor: np.ndarray, position: np.ndarray, scale: np.ndarray, rotation: np.ndarray,
+                       cx, cy) -> np.ndarray:
+    """``_layer_matrices`` with the origin vector given per sample (scalars or (N,) arrays), so the
+    samples of several layers can share one call."""
     n = len(rotation)
-    eye = np.zeros((n, 3, 3), dtype=np.float64)
-    eye[:, 0, 0] = eye[:, 1, 1] = eye[:, 2, 2] = 1.0
-    T1 = eye.copy()
+    T1 = np.zeros((n, 3, 3), dtype=np.float64)
+    T1[:, 0, 0] = T1[:, 1, 1] = T1[:, 2, 2] = 1.0
+    SR = T1.copy()
+    T2 = T1.copy()
     T1[:, 0, 2] = position[:, 0] + anchor[:, 0]
     T1[:, 1, 2] = position[:, 1] + anchor[:, 1]
     angle = (2 * np.pi * rotation) / 360
     cos_t, sin_t = np.cos(angle), np.sin(angle)
-    SR = eye.copy()
     SR[:, 0, 0] = scale[:, 0] * cos_t
     SR[:, 0, 1] = -scale[:, 0] * sin_t
     SR[:, 1, 0] = scale[:, 1] * sin_t
     SR[:, 1, 1] = scale[:, 1] * cos_t
-    cx, cy = Direction.to_vector(origin, (float(size[0]), float(size[1])))
-    T2 = eye
     T2[:, 0, 2] = -anchor[:, 0] - cx
     T2[:, 1, 2] = -anchor[:, 1] - cy
     return T1 @ SR @ T2
@@ -65,13 +71,29 @@ def _layer_matrices(anchor: np.ndarray, position: np.ndarray, scale: np.ndarray,
 def plan_affine(samples: TransformSamples, size: tuple[int, int], preview_level: int = 1) -> AffinePlan:
     """Vectorised ``_get_fixed_affine_matrix`` (composition.py:873-907) for a layer of
     ``size = (w, h)`` over all the frames in ``samples``."""
-    w, h = size
-    M = _layer_matrices(samples.anchor_point, samples.position, samples.scale, samples.rotation,
-                        samples.origin_point, size)
+    cx, cy = Direction.to_vector(samples.origin_point, (float(size[0]), float(size[1])))
+    return plan_affine_xy(samples.anchor_point, samples.position, samples.scale, samples.rotation, cx, cy,
+                          float(size[0]), float(size[1]), preview_level)
+
+
+def plan_affine_xy(anchor: np.ndarray, position: np.ndarray, scale: np.ndarray, rotation: np.ndarray, cx, cy, w, h,
+                   preview_level: int = 1) -> AffinePlan:
+    """``plan_affine`` on raw sample arrays; the origin vector ``(cx, cy)`` and the layer size ``(w, h)`` may
+    be scalars or (N,) arrays, so one call can plan the samples of MANY layers (the cost of planning is a
+    fixed number of small numpy calls, not their size).  Every sample is computed by the same float
+    operations as in a call of its own."""
+    M = _layer_matrices_xy(anchor, position, scale, rotation, cx, cy)
+    n = len(M)
     inv_l = 1 / preview_level
-    P = np.array([[inv_l, 0, 0], [0, inv_l, 0], [0, 0, 1]], dtype=np.float64)
-    A = (P @ M)[:, :2]
-    corners = np.array([[0, 0, 1], [0, h, 1], [w, 0, 1], [w, h, 1]], dtype=np.float64)
+    if preview_level == 1:
+        A = M[:, :2]   # P is the identity: P @ M differs from M at most in the sign of zeros, which ceil / floor ignore
+    else:
+        P = np.array([[inv_l, 0, 0], [0, inv_l, 0], [0, 0, 1]], dtype=np.float64)
+        A = (P @ M)[:, :2]
+    corners = np.zeros((n, 4, 3), dtype=np.float64)          # (0, 0, 1), (0, h, 1), (w, 0, 1), (w, h, 1) per sample
+    corners[:, :, 2] = 1.0
+    corners[:, 1, 1] = corners[:, 3, 1] = h
+    corners[:, 2, 0] = corners[:, 3, 0] = w
     cg = corners @ A.transpose(0, 2, 1)                      # (N, 4, 2)
     lo = np.ceil(cg.min(axis=1))
     hi = np.floor(cg.max(axis=1))
@@ -81,7 +103,7 @@ def plan_affine(samples: TransformSamples, size: tuple[int, int], preview_level:
     # at a fractional position) make cv2 fall back to "dsize = source size"; that glitch is the
     # one intentional divergence: such layers are skipped too.
     valid = (wh[:, 0] > 0) & (wh[:, 1] > 0)
-    Pf = np.zeros((len(off), 3, 3), dtype=np.float64)
+    Pf = np.zeros((n, 3, 3), dtype=np.float64)
     Pf[:, 0, 0] = Pf[:, 1, 1] = inv_l
     Pf[:, 2, 2] = 1.0
     Pf[:, 0, 2] = -off[:, 0]

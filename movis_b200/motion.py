@@ -100,8 +100,19 @@ def _ease_many(func: Callable[[float], float], t: np.ndarray) -> np.ndarray:
     if func is flat:
         return np.zeros_like(t)
     # numpy's vectorised power is not guaranteed to round like libm's pow; go through Python
-    # floats so every element takes the scalar code path the reference takes.
-    return np.array([func(v) for v in t.tolist()], dtype=np.float64)
+    # floats so every element takes the scalar code path the reference takes.  The power easings are
+    # written out per kind (the same float operations as _PowerEase.__call__, without a call per element).
+    tl = t.tolist()
+    if type(func) is _PowerEase:
+        n = func.n
+        if func.kind == "in":
+            out = [v ** n for v in tl]
+        elif func.kind == "out":
+            out = [1.0 - (1.0 - v) ** n for v in tl]
+        else:
+            out = [0.5 * (2 * v) ** n if v < 0.5 else 1.0 - 0.5 * (1.0 - 2 * (v - 0.5)) ** n for v in tl]
+        return np.array(out, dtype=np.float64)
+    return np.array([func(v) for v in tl], dtype=np.float64)
 
 
 class Motion:
@@ -149,6 +160,13 @@ class Motion:
             out[:] = first
             return out
         kf = np.asarray(self.keyframes, dtype=np.float64)
+        if len(times) and kf[0] <= times.min() and times.max() < kf[1]:
+            # every time inside the first segment (the common case: two keyframes spanning the range):
+            # the same per-element operations as below without the masks
+            span = self.keyframes[1] - self.keyframes[0]
+            t = _ease_many(self.easings[0], (times - self.keyframes[0]) / span)
+            a, b = self.values[0], self.values[1]
+            return a[None, :] + (b - a)[None, :] * t[:, None]
         hi = np.searchsorted(kf, times, side="right")
         before = times < kf[0]
         after = kf[-1] <= times

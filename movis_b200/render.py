@@ -21,7 +21,7 @@ import torch
 
 from . import _native
 from .device import require_cuda, stream_ptr
-from .layer.composition import Composition, LayerItem, fill_descriptors, plan_affine
+from .layer.composition import Composition, LayerItem, fill_descriptors, plan_affine, plan_affine_xy
 
 
 PLAN_CHUNK = 256                 # most frames planned per host step of render_frames
@@ -167,6 +167,7 @@ def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
     n = len(times)
     L = comp.preview_level
     per_layer = []  # (frame indices, descriptor rows) per layer, in paint order
+    static_jobs = []  # (slot in per_layer, frame indices, inside mask, image, samples) of the static-content layers
     keep: list = []
     for item in comp.layers:
         if not item.visible:
@@ -183,12 +184,9 @@ def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
             image = item.fg_image_device(float(times[idx[inside][0]]), comp.cache) if inside.any() else None
             if image is None:
                 continue
-            rows = np.zeros(len(idx), dtype=_native.LAYER_DTYPE)
-            plan = plan_affine(samples, (image.shape[1], image.shape[0]), L)
-            fill_descriptors(rows, image, plan, samples.opacity, samples.blending_mode)
-            sel = inside & plan.valid
             keep.append(image)
-            per_layer.append((idx[sel], rows[sel]))
+            static_jobs.append((len(per_layer), idx, inside, image, samples))
+            per_layer.append(None)   # filled in below, by ONE affine plan for all static layers
             continue
         # general case: the image may change per frame (sequences, nested comps, animated effects)
         rows = np.zeros(len(idx), dtype=_native.LAYER_DTYPE)
@@ -233,6 +231,27 @@ def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
             ok[js_arr] = plan.valid
             keep.extend(images[j] for j in js)
         per_layer.append((idx[ok], rows[ok]))
+
+    if static_jobs:
+        # The affine set-up of every static layer in one call: its cost is a fixed number of small numpy
+        # calls whatever the number of samples, so 16 layers x 150 frames cost what one layer does.
+        from .enum import Direction
+        lens = [len(job[1]) for job in static_jobs]
+        cat = lambda field: np.concatenate([getattr(job[4], field) for job in static_jobs])   # noqa: E731
+        sizes = [(job[3].shape[1], job[3].shape[0]) for job in static_jobs]
+        origin = [Direction.to_vector(job[4].origin_point, (float(w), float(h))) for job, (w, h) in zip(static_jobs, sizes)]
+        rep = lambda vals: np.repeat(np.asarray(vals, dtype=np.float64), lens)   # noqa: E731
+        plan = plan_affine_xy(cat("anchor_point"), cat("position"), cat("scale"), cat("rotation"),
+                              rep([o[0] for o in origin]), rep([o[1] for o in origin]),
+                              rep([sz[0] for sz in sizes]), rep([sz[1] for sz in sizes]), L)
+        start = 0
+        for (slot, idx, inside, image, samples), m in zip(static_jobs, lens):
+            one = type(plan)(plan.matrix[start:start + m], plan.bbox[start:start + m], plan.valid[start:start + m])
+            rows = np.zeros(m, dtype=_native.LAYER_DTYPE)
+            fill_descriptors(rows, image, one, samples.opacity, samples.blending_mode)
+            sel = inside & one.valid
+            per_layer[slot] = (idx[sel], rows[sel])
+            start += m
 
     counts = np.zeros(n, dtype=np.int64)
     for frames, _ in per_layer:
