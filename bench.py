@@ -542,8 +542,11 @@ def run_s5(world: int, rank: int, weights=None) -> dict:
     from movis_b200.render import render_frames, shard_range, stream_frames
     N = 1800
     comp = scenes.build_s5(mv, ChromaKey)
-    mine = shard_range(N, rank, world)
-    times = np.asarray(mine, dtype=np.float64) / FPS
+    from movis_b200.render import frame_costs
+    all_times = np.arange(N, dtype=np.float64) / FPS
+    # device leg: contiguous ranges of equal estimated cost (the layers grow over the timeline)
+    mine = shard_range(N, rank, world, costs=frame_costs(comp, all_times) if world > 1 else None)
+    times = all_times[mine.start:mine.stop]
     for _ in stream_frames(comp, times[:16], bg_color=BG, copy=False):   # warm-up: uploads, effect caches
         pass
     CALL = 240   # frames per render_frames call (8 GB of frames resident; the call plans 240 frames at once)

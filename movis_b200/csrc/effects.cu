@@ -433,6 +433,7 @@ struct PointParams {
     const uint8_t* src;
     uint8_t* dst;
     int32_t w, h, sstride, dstride;
+    uint32_t rcp_mul, rcp_shift;   // i / vectors_per_row == umulhi(i, rcp_mul) >> rcp_shift (rcp_mul == 0: one vector per row)
     int32_t op;          // 0 chroma key, 1 fill colour, 2 HSL shift
     uint32_t color;      // fill colour (packed rgb)
     uint8_t lo[4], hi[4];
@@ -470,10 +471,12 @@ __global__ void __launch_bounds__(256) k_pointwise(const __grid_constant__ Point
         s_luts[512 + threadIdx.x] = P.vlut[threadIdx.x];
         __syncthreads();
     }
-    const int per_row = (P.w + VEC - 1) / VEC;
-    const long long total = (long long)per_row * P.h;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int y = (int)(i / per_row), x = (int)(i - (long long)y * per_row) * VEC;
+    const uint32_t per_row = (uint32_t)(P.w + VEC - 1) / VEC;
+    const uint32_t total = per_row * (uint32_t)P.h;                    // (the host keeps it below 2^31)
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        // row / column of vector i by a multiply-high with the host's reciprocal of the row length (no 64-bit division)
+        const uint32_t yy = P.rcp_mul ? __umulhi(i, P.rcp_mul) >> P.rcp_shift : i;
+        const int y = (int)yy, x = (int)(i - yy * per_row) * VEC;
         const uint8_t* sp = P.src + (int64_t)y * P.sstride + (int64_t)x * 4;
         uint8_t* dp = P.dst + (int64_t)y * P.dstride + (int64_t)x * 4;
         if (VEC == 4 && x + 4 <= P.w) {
@@ -752,6 +755,17 @@ extern "C" int mvb_effect_drop_shadow_rgba8(const void* src, int32_t w, int32_t 
     return check_launch("mvb_effect_drop_shadow_rgba8");
 }
 
+// floor(i / d) = umulhi(i, m) >> (l - 1) with l = ceil(log2 d), m = ceil(2^(31 + l) / d) <= 2^32 - 1 for d > 1:
+// m d - 2^(31 + l) < d <= 2^l, so the error term i (m d - 2^(31 + l)) stays below 2^(31 + l) for i < 2^31.
+// d == 1 is flagged by m == 0.
+static void row_reciprocal(uint64_t d, uint32_t& mul, uint32_t& shift)
+{
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    mul = d == 1 ? 0u : (uint32_t)(((1ull << (31 + l)) + d - 1) / d);
+    shift = d == 1 ? 0u : l - 1;
+}
+
 static int launch_pointwise(PointParams& P, const void* src, int w, int h, int64_t sstride, void* dst,
                             int64_t dstride, mvb_stream_t stream, const char* what)
 {
@@ -764,7 +778,9 @@ static int launch_pointwise(PointParams& P, const void* src, int w, int h, int64
     P.w = w; P.h = h; P.sstride = (int32_t)sstride; P.dstride = (int32_t)dstride;
     const bool vec = !((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
                         (uintptr_t)sstride | (uintptr_t)dstride) & 15);
-    const long long work = (long long)((w + (vec ? 3 : 0)) / (vec ? 4 : 1)) * h;
+    const long long per_row = (w + (vec ? 3 : 0)) / (vec ? 4 : 1), work = per_row * h;
+    if (work >= (1ll << 31)) return set_error(MVB_ERR_UNSUPPORTED, "image too large");
+    row_reciprocal((uint64_t)per_row, P.rcp_mul, P.rcp_shift);
     const int blocks = (int)std::min<long long>((work + 255) / 256, 148 * 8);
     if (vec) k_pointwise<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
     else k_pointwise<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
@@ -835,13 +851,7 @@ extern "C" int mvb_effect_chroma_key_rgba8(const void* src, int32_t w, int32_t h
     if (total >= (1ull << 31)) return set_error(MVB_ERR_UNSUPPORTED, "image too large");
     C.per_row = (uint32_t)per_row;
     C.total = (uint32_t)total;
-    // floor(i / d) = umulhi(i, m) >> (l - 1) with l = ceil(log2 d), m = ceil(2^(31 + l) / d) <= 2^32 - 1 for d > 1:
-    // m d - 2^(31 + l) < d <= 2^l, so the error term i (m d - 2^(31 + l)) stays below 2^(31 + l) for i < 2^31.
-    // d == 1 is flagged by m == 0.
-    uint32_t l = 0;
-    while ((1ull << l) < per_row) ++l;
-    C.rcp_mul = per_row == 1 ? 0u : (uint32_t)(((1ull << (31 + l)) + per_row - 1) / per_row);
-    C.rcp_shift = per_row == 1 ? 0u : l - 1;
+    row_reciprocal(per_row, C.rcp_mul, C.rcp_shift);
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const unsigned grid = (unsigned)std::min<uint64_t>((total + 511) / 512, (uint64_t)n_sm * 6);

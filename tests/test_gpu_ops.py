@@ -262,8 +262,13 @@ def test_pointwise_effects_vs_oracle_ragged_widths(dev):
     dev = to_device(wide)
     for x0, ww in ((0, 300), (4, 256), (8, 100), (3, 97), (12, 4), (1, 1), (16, 960 // 4)):
         view = dev[2:35, x0:x0 + ww]
+        host = np.ascontiguousarray(wide[2:35, x0:x0 + ww])
         got = ChromaKey().apply_device(view, 0.0).cpu().numpy()
-        assert np.array_equal(got, O.effect_chroma_key(np.ascontiguousarray(wide[2:35, x0:x0 + ww]))), (x0, ww)
+        assert np.array_equal(got, O.effect_chroma_key(host)), (x0, ww)
+        got = mv.effect.HSLShift(77.0, -0.2, 0.3).apply_device(view, 0.0).cpu().numpy()
+        assert np.array_equal(got, O.effect_hsl_shift(host, 77.0, -0.2, 0.3)), (x0, ww)
+        got = mv.effect.FillColor((9, 200, 30)).apply_device(view, 0.0).cpu().numpy()
+        assert np.array_equal(got, O.effect_fill_color(host, (9, 200, 30))), (x0, ww)
     full = rng.integers(0, 256, (2160, 3840, 4), dtype=np.uint8)  # config-4 sized green screen
     full[:1080, :, :3] = (0, 255, 0)
     got = ChromaKey()(full, 0.0)

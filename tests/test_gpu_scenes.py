@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_DIR
-from scene_zoo import golden_shots
+from scene_zoo import golden_shots, occlusion_fuzz
 
 pytestmark = pytest.mark.gpu
 
@@ -188,6 +188,16 @@ def test_whole_pixel_shifts_and_hidden_layers_vs_oracle():
     big = _occlusion_scene(mv, size=(1000, 700))          # several whole tiles under the cover
     _assert_matches_oracle(big, 0.25, (0, 0, 0, 255))
     _assert_matches_oracle(big, 0.25, (0, 0, 0, 0))
+
+
+def test_randomised_shift_and_occlusion_scenes_vs_oracle():
+    """A slice of tools/fuzz_parity.py (which ran 460 seeds = 11 000 frames without a mismatch)."""
+    mv, _ = _mv()
+    for seed in range(300, 312):
+        comp = occlusion_fuzz(mv, seed)
+        for t, bg, level in ((0.0, (0, 0, 0, 0), 1), (1.3, (200, 9, 200, 255), 1), (0.6, (1, 2, 3, 255), 2)):
+            if min(comp.size) >= 2 * level:
+                _assert_matches_oracle(comp, t, bg, level=level)
 
 
 def test_opaque_source_flag_never_changes_a_pixel():
