@@ -1,11 +1,14 @@
-// stack_float.cuh -- the fused warp + blend kernel for OPAQUE frames (bg_color alpha 255), sm_100a.
+// stack_float.cuh -- arithmetic of the fused warp + blend kernel (k_stack_frames, stack_frames.cuh), sm_100a:
+// exact float forms of cv2's bilinear, of both "over" operators and of the 18 blend modes, the TMA /
+// mbarrier plumbing, and walk_layer, one layer of the walk for one thread.
 //
-// Same contract as k_composite_stack (composite.cu): per frame it replaces the reference's
-// cv2.warpAffine -> alpha_composite pair of every layer (movis/layer/composition.py:811-819) and
-// the frame walk around it (composition.py:363-368), bit for bit.  An opaque background keeps the
-// frame's alpha at 255 through every layer (both "over" operators map dst alpha 255 to 255), so
-// both reduce to   out = floor((fa*T + (255-fa)*b [+127 for PIL]) / 255)   per colour channel
-// (imgproc.py:156-165 with oa = 65025; PIL's ImagingAlphaComposite with outa255 = 65025).
+// Contract: per frame the kernel replaces the reference's cv2.warpAffine -> alpha_composite pair of every
+// layer (movis/layer/composition.py:811-819) and the frame walk around it (composition.py:363-368), bit
+// for bit.  An opaque background keeps the frame's alpha at 255 through every layer (both "over"
+// operators map dst alpha 255 to 255), so on OPAQUE frames both reduce to
+//     out = floor((fa*T + (255-fa)*b [+127 for PIL]) / 255)   per colour channel
+// (imgproc.py:156-165 with oa = 65025; PIL's ImagingAlphaComposite with outa255 = 65025); translucent
+// frames carry alpha as a fourth channel and use the general forms (over_numpy_rows / over_pil_rows).
 //
 // Why float: on B200 the kernel is bound by instruction issue, not HBM (tools/experiments/
 // pipe_rates*.cu: LOP3/SHF/PRMT/IMAD/IDP issue at 0.5 per clock per scheduler, IMAD.HI at 0.21,
@@ -514,9 +517,7 @@ __device__ __forceinline__ void walk_layer(const FrameGeom& G, const DevLayer* _
             down[q] = pitch;
             if (PART && !(ok >> q & 1)) { a[q] = smem_addr(softg); down[q] = 0u; wt[q] = wb[q] = 0u; }
         }
-#ifndef MVB_DIAG_NOWAIT   // (diagnostic build: how fast the consumers are when they never wait for a box)
         mbar_wait((uint32_t)info.y, (info.x >> 11) & 1);
-#endif
 #pragma unroll
         for (int q = 0; q < ROWS; ++q) {
             t[q][0] = lds_u32(a[q]);

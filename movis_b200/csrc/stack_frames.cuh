@@ -302,9 +302,6 @@ k_stack_frames(const __grid_constant__ FramesParams P)
             if (lane < ns) {
                 while (my_head < g) {
                     if (my_k > 0 && !mbar_test(bar_empty + 8 * lane, (my_k - 1) & 1)) break;
-#ifdef MVB_DIAG_NOWAIT   // (the consumers do not wait for the box: the previous one must have landed before the barrier is re-armed)
-                    if (my_k > 0 && !mbar_test(bar_full + 8 * lane, (my_k - 1) & 1)) break;
-#endif
                     const int4 r = s_req[my_head & (kWsUnits * kWsSlots - 1)];
                     mbar_arrive_expect_tx(bar_full + 8 * lane, (uint32_t)r.y);
                     tma_load_box(stage0 + lane * P.stage_bytes, &P.maps[r.x], r.z, r.w, bar_full + 8 * lane);
