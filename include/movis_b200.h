@@ -121,7 +121,8 @@ typedef struct mvb_layer {
  * then warp + blend every layer in paint order, fused into one pass over the frame (each output
  * tile walks the layer stack in registers; the frame is written once).
  * `layers` is a HOST array.  Results are bit-identical to running the reference's
- * warpAffine -> alpha_composite pair per layer.
+ * warpAffine -> alpha_composite pair per layer.  Frames and layer sources are limited to 32767 px
+ * per side (MVB_ERR_UNSUPPORTED beyond).
  * The library keeps a small device scratch buffer per (device, stream) for cv2's coordinate tables
  * (8 bytes x (width + height) per layer); calls that share a stream must not be made concurrently
  * from several host threads.

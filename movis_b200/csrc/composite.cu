@@ -551,6 +551,8 @@ static int launch_run(int nF, void* const* frames, const int32_t* beg, const int
 static int launch_frames(int n_frames, void* const* frames, int W, int H, int64_t stride, const uint8_t bg[4],
                          const int32_t* offsets, const mvb_layer* layers, int flags, cudaStream_t stream)
 {
+    // (tile origins travel as 16-bit halves of one word, k_stack_prep's list header)
+    if (W > 32767 || H > 32767) return set_error(MVB_ERR_UNSUPPORTED, "frames are limited to 32767 px per side");
     // An opaque bg_color keeps the frame's alpha at 255 through every layer (both "over" operators
     // map dst alpha 255 to 255), so the division-free kernel instantiation applies.
     const bool keep = (flags & MVB_STACK_KEEP_FRAME) != 0;
