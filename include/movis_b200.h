@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MVB_ABI_VERSION 1
+#define MVB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MVB_API __attribute__((visibility("default")))
@@ -114,6 +114,11 @@ typedef struct mvb_layer {
     int32_t blend_mode;   /* MVB_BLEND_* */
     int32_t flags;        /* MVB_LAYER_* */
     double opacity;       /* TransformValue.opacity in [0, 1] */
+    const void* alpha_map; /* optional (NULL: none): device pointer to the source's alpha map written by
+                            * mvb_alpha_map_rgba8 -- ceil(src_h / 32) rows of ceil(src_w / 32) bytes, the largest
+                            * alpha of each 32 x 32 block.  Pure work elimination: tiles whose taps all fall into
+                            * blocks of alpha 0 skip the layer where that cannot change a pixel (PIL over, or an
+                            * opaque frame); keyed-out green screens, sprites with wide transparent margins. */
 } mvb_layer;
 
 /*
@@ -146,6 +151,12 @@ MVB_API int mvb_composite_frames(int32_t n_frames, void* const* frames, int32_t 
 MVB_API int mvb_warp_affine_rgba8(const void* src, int32_t src_w, int32_t src_h, int64_t src_stride,
                           void* dst, int32_t dst_w, int32_t dst_h, int64_t dst_stride,
                           const double M[6], mvb_stream_t stream);
+
+/* The alpha map of an RGBA8 image for mvb_layer.alpha_map: map[(y / 32) * ceil(w / 32) + x / 32] = the
+ * largest alpha among the pixels of that 32 x 32 block.  No counterpart in the reference (its warpAffine /
+ * alpha_composite pair always touches every pixel of the layer's bbox, composition.py:811-819). */
+MVB_API int mvb_alpha_map_rgba8(const void* src, int32_t w, int32_t h, int64_t stride, void* map,
+                        mvb_stream_t stream);
 
 /* movis.imgproc.alpha_composite(bg, fg, position, opacity, blending_mode, matte_mode)
  * (imgproc.py:216-273).  bg is updated in place.  flags: MVB_LAYER_PIL_OVER selects the PIL

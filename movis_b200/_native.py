@@ -20,14 +20,14 @@ MVB_LAYER_OPAQUE_SOURCE = 2
 MVB_STACK_KEEP_FRAME = 1
 MVB_BLUR_PLAIN, MVB_BLUR_GLOW = 0, 1
 
-# numpy mirror of `struct mvb_layer` (104 bytes, natural alignment)
+# numpy mirror of `struct mvb_layer` (112 bytes, natural alignment)
 LAYER_DTYPE = np.dtype([
     ("src", np.uint64), ("src_w", np.int32), ("src_h", np.int32), ("src_stride", np.int64),
     ("M", np.float64, (6,)),
     ("bbox_x", np.int32), ("bbox_y", np.int32), ("bbox_w", np.int32), ("bbox_h", np.int32),
-    ("blend_mode", np.int32), ("flags", np.int32), ("opacity", np.float64),
+    ("blend_mode", np.int32), ("flags", np.int32), ("opacity", np.float64), ("alpha_map", np.uint64),
 ], align=True)
-assert LAYER_DTYPE.itemsize == 104
+assert LAYER_DTYPE.itemsize == 112
 
 # every symbol include/movis_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "mvb_blur_ksize", "mvb_gaussian_weights_q8", "mvb_effect_blur_scratch_bytes",
     "mvb_effect_blur_rgba8", "mvb_effect_drop_shadow_rgba8", "mvb_effect_chroma_key_rgba8",
     "mvb_effect_fill_color_rgba8", "mvb_effect_hsl_shift_rgba8", "mvb_rgb_to_hsv_u8",
-    "mvb_source_stripe_rgba8",
+    "mvb_source_stripe_rgba8", "mvb_alpha_map_rgba8",
 ]
 
 
@@ -68,6 +68,7 @@ def lib():
     L.mvb_composite_frames.argtypes = [i32, vp, i32, i32, i64, u8p, vp, vp, i32, vp]
     L.mvb_warp_affine_rgba8.argtypes = [vp, i32, i32, i64, vp, i32, i32, i64, vp, vp]
     L.mvb_alpha_composite.argtypes = [vp, i32, i32, i64, vp, i32, i32, i64, i32, i32, dbl, i32, i32, i32, vp]
+    L.mvb_alpha_map_rgba8.argtypes = [vp, i32, i32, i64, vp, vp]
     L.mvb_blur_ksize.argtypes = [dbl]
     L.mvb_blur_ksize.restype = i32
     L.mvb_gaussian_weights_q8.argtypes = [dbl, i32, vp]

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from .. import _native
-from ..device import empty_image, image_args, stream_ptr
+from ..device import attach_alpha_map, empty_image, image_args, stream_ptr
 from ..effect.protocol import DeviceEffectMixin
 from ..util import to_rgb
 
@@ -44,4 +44,5 @@ class ChromaKey(DeviceEffectMixin):
         _native.check(_native.lib().mvb_effect_chroma_key_rgba8(
             ptr, w, h, stride, out.data_ptr(), out.stride(0), self._lower_color.ctypes.data,
             self._upper_color.ctypes.data, stream_ptr()))
-        return out
+        # keyed-out regions are what a chroma key is for: let the compositor skip them tile by tile
+        return attach_alpha_map(out)

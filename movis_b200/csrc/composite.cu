@@ -56,12 +56,13 @@ struct DevLayer {
     // --- the rest ---
     const uint8_t* src;
     float* lut;           // 256 floats of this layer in the run's scratch (written only with kLayerLut)
+    const uint8_t* amap;  // mvb_layer::alpha_map or null
     int32_t src_stride;
     int32_t pil_a;        // int(round(opacity * 255)) for the PIL path (imgproc.py:207)
     double m[6];          // inverse map: bbox px -> layer px (OpenCV's own inversion, done on host)
     double opacity;
 };
-static_assert(sizeof(DevLayer) == 160 && offsetof(DevLayer, src) == 80 && offsetof(DevLayer, opac_c) == 64 &&
+static_assert(sizeof(DevLayer) == 168 && offsetof(DevLayer, src) == 80 && offsetof(DevLayer, opac_c) == 64 &&
               offsetof(DevLayer, map_index) == 72, "descriptor layout");
 
 // soft_light's table (see blend_diff2<11>, stack_float.cuh): 256 pairs (A, R), a compile-time constant.
@@ -166,6 +167,7 @@ static int fill_dev_layer(const mvb_layer& in, DevLayer& out)
     if (!(in.opacity >= 0.0 && in.opacity <= 1.0))
         return set_error(MVB_ERR_INVALID_ARG, "opacity must be in [0, 1]");
     out.src = static_cast<const uint8_t*>(in.src);
+    out.amap = static_cast<const uint8_t*>(in.alpha_map);
     out.src_w = in.src_w;
     out.src_h = in.src_h;
     out.src_stride = (int32_t)in.src_stride;
@@ -602,6 +604,43 @@ static int launch_frames(int n_frames, void* const* frames, int W, int H, int64_
 } // namespace mvb
 
 using namespace mvb;
+
+// One CTA per 32 x 32 block of the image: the largest alpha of the block (mvb_layer::alpha_map).
+__global__ void __launch_bounds__(256)
+k_alpha_map(const uint8_t* __restrict__ src, int w, int h, int64_t stride, uint8_t* __restrict__ map, int gw)
+{
+    __shared__ uint32_t s_max[8];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int x = bx + (threadIdx.x & 31);
+    uint32_t m = 0;
+    if (x < w) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int y = by + (threadIdx.x >> 5) * 4 + r;
+            if (y < h) m = max(m, reinterpret_cast<const uint32_t*>(src + (int64_t)y * stride)[x] >> 24);
+        }
+    }
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m = max(m, s_max[i]);
+        map[(size_t)blockIdx.y * (size_t)gw + blockIdx.x] = (uint8_t)m;
+    }
+}
+
+extern "C" int mvb_alpha_map_rgba8(const void* src, int32_t w, int32_t h, int64_t stride, void* map, mvb_stream_t stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_image(src, w, h, stride, "src")) return rc;
+    if (!map) return set_error(MVB_ERR_INVALID_ARG, "map is null");
+    const int gw = (w + 31) / 32, gh = (h + 31) / 32;
+    k_alpha_map<<<dim3((unsigned)gw, (unsigned)gh), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint8_t*>(src), w, h, stride, static_cast<uint8_t*>(map), gw);
+    count_launches(1);
+    return check_launch("mvb_alpha_map_rgba8");
+}
 
 extern "C" int mvb_max_layers_per_launch(void) { return kMaxLayers; }
 

@@ -153,7 +153,20 @@ k_stack_prep(const PrepParams T)
                         u1 == min(tx0 + kTileW, T.W) - 1 - bx && v1 == min(ty0 + T.tile_h, T.H) - 1 - by;
                 // No tap inside the source: every sample is transparent.  A no-op for PIL's over and on an
                 // opaque frame; numpy's over still zeroes rgb where the frame's alpha is 0 (imgproc.py:164).
-                const bool nothing = xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f;
+                bool nothing = xmax < -1.25f || xmin > src_w + 0.25f || ymax < -1.25f || ymin > src_h + 0.25f;
+                // ... or every tap falls into 32 x 32 blocks of the source whose alpha is 0 throughout (the
+                // layer's alpha map, if it has one): the same "every sample is transparent"
+                if (!nothing && L.amap) {
+                    const int cx0 = max((int)floorf(xmin) - 1, 0) >> 5, cx1 = min((int)floorf(xmax) + 2, src_w - 1) >> 5;
+                    const int cy0 = max((int)floorf(ymin) - 1, 0) >> 5, cy1 = min((int)floorf(ymax) + 2, src_h - 1) >> 5;
+                    if (cx0 <= cx1 && cy0 <= cy1 && (cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 16) {
+                        const int gw = (src_w + 31) >> 5;
+                        uint32_t seen = 0;
+                        for (int cy = cy0; cy <= cy1; ++cy)
+                            for (int cx = cx0; cx <= cx1; ++cx) seen |= __ldg(L.amap + cy * gw + cx);
+                        nothing = seen == 0;
+                    }
+                }
                 if (!(nothing && (T.opaque || (L.flags & kLayerPil)))) {
                     cls = kTileEdge;
                     // taps span [floor(xmin) - 1, floor(xmax) + 2] at most (same slack as above); TMA wants

@@ -120,8 +120,25 @@ def upload_source(image: np.ndarray) -> torch.Tensor:
     tensor object only: views, crops and effect outputs do not inherit it."""
     t = to_device(image)
     # on the device, right behind the copy: 50 us, where numpy needs milliseconds per 4K image
-    if t.numel() and int(t[..., 3].min().item()) == 255:
-        t.mvb_opaque = True
+    if t.numel():
+        lowest = int(t[..., 3].min().item())
+        if lowest == 255:
+            t.mvb_opaque = True
+        elif lowest == 0:
+            attach_alpha_map(t)
+    return t
+
+
+def attach_alpha_map(t: torch.Tensor) -> torch.Tensor:
+    """Compute the alpha map of a device image (the largest alpha of every 32 x 32 block,
+    ``mvb_alpha_map_rgba8``) and keep it on the tensor object: ``fill_descriptors`` hands it to the fused
+    kernel, which then skips the layer in tiles that only see fully transparent blocks (a keyed-out green
+    screen, the margins of a sprite).  Work elimination only; views and effect outputs do not inherit it."""
+    from . import _native
+    ptr, w, h, stride = image_args(t)
+    grid = torch.empty(((h + 31) // 32, (w + 31) // 32), dtype=torch.uint8, device=t.device)
+    _native.check(_native.lib().mvb_alpha_map_rgba8(ptr, w, h, stride, grid.data_ptr(), stream_ptr()))
+    t.mvb_alpha_map = grid
     return t
 
 

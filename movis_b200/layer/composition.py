@@ -149,6 +149,8 @@ def fill_descriptors(out: np.ndarray, image, plan: AffinePlan, opacity: np.ndarr
     if getattr(image, "mvb_opaque", False):   # device.upload_source: alpha is 255 throughout
         flags |= _native.MVB_LAYER_OPAQUE_SOURCE
     out["flags"] = flags
+    amap = getattr(image, "mvb_alpha_map", None)   # device.attach_alpha_map: blocks of alpha 0 are skipped
+    out["alpha_map"] = 0 if amap is None else amap.data_ptr()
     out["opacity"] = opacity
 
 

@@ -227,6 +227,8 @@ def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
             group["src_stride"] = [images[j].stride(0) for j in js]
             opaque = np.fromiter((bool(getattr(images[j], "mvb_opaque", False)) for j in js), dtype=bool, count=len(js))
             group["flags"] = (group["flags"] & ~_native.MVB_LAYER_OPAQUE_SOURCE) | np.where(opaque, _native.MVB_LAYER_OPAQUE_SOURCE, 0)
+            maps = [getattr(images[j], "mvb_alpha_map", None) for j in js]
+            group["alpha_map"] = [0 if m is None else m.data_ptr() for m in maps]
             rows[js_arr] = group
             ok[js_arr] = plan.valid
             keep.extend(images[j] for j in js)

@@ -24,15 +24,15 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/movis_b200.h but not exported"
     assert sorted(_native.EXPORTED_SYMBOLS) == names
-    assert lib.mvb_abi_version() == 1 and lib.mvb_max_layers_per_launch() >= 16
+    assert lib.mvb_abi_version() == 2 and lib.mvb_max_layers_per_launch() >= 16
 
 
 def test_layer_struct_layout_matches_header():
     dt = _native.LAYER_DTYPE
     offs = {n: dt.fields[n][1] for n in dt.names}
     assert offs == {"src": 0, "src_w": 8, "src_h": 12, "src_stride": 16, "M": 24, "bbox_x": 72, "bbox_y": 76,
-                    "bbox_w": 80, "bbox_h": 84, "blend_mode": 88, "flags": 92, "opacity": 96}
-    assert dt.itemsize == 104
+                    "bbox_w": 80, "bbox_h": 84, "blend_mode": 88, "flags": 92, "opacity": 96, "alpha_map": 104}
+    assert dt.itemsize == 112
 
 
 def test_host_helpers_agree_with_oracle():

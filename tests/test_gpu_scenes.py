@@ -21,6 +21,9 @@ from scene_zoo import golden_shots, occlusion_fuzz
 pytestmark = pytest.mark.gpu
 
 
+from movis_b200.scenes import BLEND_MODE_NAMES as BLEND_NAMES, synthetic_rgba as scenes_rgba  # noqa: E402
+
+
 def _mv():
     import movis_b200 as mv
     from movis_b200.contrib.segmentation import ChromaKey
@@ -198,6 +201,49 @@ def test_randomised_shift_and_occlusion_scenes_vs_oracle():
         for t, bg, level in ((0.0, (0, 0, 0, 0), 1), (1.3, (200, 9, 200, 255), 1), (0.6, (1, 2, 3, 255), 2)):
             if min(comp.size) >= 2 * level:
                 _assert_matches_oracle(comp, t, bg, level=level)
+
+
+def test_alpha_map_skips_transparent_blocks_without_changing_a_pixel():
+    """mvb_alpha_map_rgba8 against numpy, and scenes of sprites with wide transparent regions (every
+    blend mode, rotated, both background alphas) rendered with and without the maps and by the oracle."""
+    import torch
+    from movis_b200 import _native
+    from movis_b200.device import attach_alpha_map, to_device
+    from movis_b200.render import launch_plan, plan_range
+    mv, _ = _mv()
+    rng = np.random.default_rng(5)
+    for h, w in ((1, 1), (31, 33), (64, 64), (100, 257)):
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        img[: h // 2, :, 3] = 0
+        img[:, w // 3: w // 2, 3] = 0
+        got = attach_alpha_map(to_device(img)).mvb_alpha_map.cpu().numpy()
+        gh, gw = (h + 31) // 32, (w + 31) // 32
+        want = np.array([[img[32 * y:32 * y + 32, 32 * x:32 * x + 32, 3].max() for x in range(gw)] for y in range(gh)], np.uint8)
+        assert np.array_equal(got, want), (h, w)
+    comp = mv.layer.Composition(size=(640, 400), duration=2.0)
+    comp.add_layer(mv.layer.Image(scenes_rgba(7000, 400, 640, "random")), name="bg", opacity=0.9)
+    for i in range(18):
+        sprite = scenes_rgba(7001 + i, 300, 420, "random")
+        sprite[:, :140, 3] = 0            # wide transparent margins and a transparent band
+        sprite[:90, :, 3] = 0
+        sprite[200:240, :, 3] = 0
+        item = comp.add_layer(mv.layer.Image(sprite), name=f"s{i}", position=(120.0 + 25 * i, 90.0 + 13 * i),
+                              rotation=11.0 * i, scale=0.7 + 0.05 * i, opacity=1.0 if i % 3 else 0.6,
+                              blending_mode=BLEND_NAMES[i])
+        item.rotation.enable_motion().extend([0.0, 2.0], [11.0 * i, 11.0 * i + 50.0])
+    for t in (0.0, 1.1):
+        for bg in ((0, 0, 0, 0), (30, 20, 10, 255)):
+            _assert_matches_oracle(comp, t, bg)
+    plan = plan_range(comp, np.array([0.3, 1.7]))
+    assert (plan.descriptors["alpha_map"] != 0).sum() >= 36
+    out = [torch.zeros((2, 400, 640, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    for bg in ((0, 0, 0, 0), (1, 2, 3, 255)):
+        launch_plan(plan, out[0], bg)
+        stripped = type(plan)(plan.descriptors.copy(), plan.offsets, plan.keepalive)
+        stripped.descriptors["alpha_map"] = 0
+        launch_plan(stripped, out[1], bg)
+        torch.cuda.synchronize()
+        assert torch.equal(out[0], out[1]), bg
 
 
 def test_opaque_source_flag_never_changes_a_pixel():
