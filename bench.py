@@ -289,16 +289,16 @@ def other_configs(peak: float) -> dict:
     comp = scenes.build_s1(mv)
     record("S1 (configs[0]: 1080p, bg + 8 rotating layers)", time_scene(comp, full, reps=4), scenes.s1_bytes_per_frame(), len(full))
     comp = scenes.build_s2d(mv)
-    record("S2d (dense: 17 full-frame 4K layers)", time_scene(comp, full[:30]), scenes.s2d_bytes_per_frame(), 30)
+    record("S2d (dense: 17 full-frame 4K layers)", time_scene(comp, full[:60]), scenes.s2d_bytes_per_frame(), 60)
     del comp
     torch.cuda.empty_cache()
     comp = scenes.build_s3(mv)
-    record("S3 (configs[2]: nested 1080p comp with blur / shadow / glow in a 4K parent)", time_scene(comp, full[:60]),
-           s3_bytes_per_frame(), 60, "effect outputs are static: computed once per range")
+    record("S3 (configs[2]: nested 1080p comp with blur / shadow / glow in a 4K parent)", time_scene(comp, full),
+           s3_bytes_per_frame(), len(full), "effect outputs are static: computed once per range")
     comp = scenes.build_s4(mv, ChromaKey)
     for level in (1, 2, 4):
-        record(f"S4 L={level} (configs[3]: chroma-keyed 4K sequence over a 4.2K background)", time_scene(comp, full[:48], level=level),
-               s4_bytes_per_frame(level), 48, "the chroma key runs as its own pass once per distinct sequence frame (8 of them; cached through ChromaKey.get_key)")
+        record(f"S4 L={level} (configs[3]: chroma-keyed 4K sequence over a 4.2K background)", time_scene(comp, full, level=level),
+               s4_bytes_per_frame(level), len(full), "the chroma key runs as its own pass once per distinct sequence frame (8 of them; cached through ChromaKey.get_key)")
     del comp
     torch.cuda.empty_cache()
     return out
