@@ -246,7 +246,12 @@ def s3_bytes_per_frame() -> int:
 
 
 def s4_bytes_per_frame(level: int) -> int:
-    return 4 * (3840 // level) * (2160 // level) + 2 * 33177600   # frame + keyed 4K frame + the bg region sampled
+    # frame + keyed 4K frame + the bg region sampled, except that a draft frame cannot need more
+    # of a source than the four 4-byte taps of each of its pixels: at level 4 the samples are 4 texels apart
+    # and three quarters of the source rows are never touched, so counting whole sources would overstate the
+    # traffic (and put the "roofline fraction" above 1)
+    out_px = (3840 // level) * (2160 // level)
+    return 4 * out_px + 2 * min(33177600, 16 * out_px)
 
 
 def s5_bytes_per_frame() -> int:

@@ -140,6 +140,10 @@ class ImageSequence(TimelineMixin):
         i = self.get_state(time)
         return i if i >= 0 else -1
 
+    def get_keys(self, times: np.ndarray) -> np.ndarray:
+        """``get_key`` for an array of times (lets the range planner fetch each distinct image once)."""
+        return self.get_states(times)
+
     def _host_image(self, i: int) -> np.ndarray:
         if self.images[i] is None:
             f = self.img_files[i]

@@ -21,6 +21,14 @@ class TimelineMixin:
             return i
         return -1
 
+    def get_states(self, times: np.ndarray) -> np.ndarray:
+        """``get_state`` for an array of times (the same comparisons, vectorised)."""
+        times = np.asarray(times, dtype=np.float64)
+        i = np.searchsorted(self.end_times, times, side="right")
+        j = np.minimum(i, len(self.start_times) - 1)
+        ok = (i < len(self.start_times)) & (self.start_times[j] <= times) & (times < self.end_times[j])
+        return np.where(ok, i, -1)
+
     @property
     def duration(self):
         return self.end_times[-1] - self.start_times[0]

@@ -161,6 +161,18 @@ def _static_content(item: LayerItem) -> bool:
     return True
 
 
+def _effects_time_invariant(item: LayerItem) -> bool:
+    """True when the effect chain of ``item`` maps equal input images to equal output images whatever
+    the time: every effect runs on the device, defines ``get_key`` and has no animated attribute."""
+    for e in item.effects:
+        if not hasattr(e, "apply_device") or not hasattr(e, "get_key"):
+            return False
+        attrs = getattr(e, "attributes", None)
+        if attrs is not None and not all(a.is_static for a in attrs.values()):
+            return False
+    return True
+
+
 def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
     """Evaluate the scene for every element of ``times`` (all inside ``[0, duration)``)."""
     times = np.asarray(times, dtype=np.float64)
@@ -206,6 +218,16 @@ def plan_range(comp: Composition, times: Sequence[float]) -> RangePlan:
                 keep.append(batch)
                 for k, j in enumerate(inside):
                     images[j] = item.apply_effects_device(batch[k], float(lt[j]))
+        elif hasattr(item.layer, "get_keys") and _effects_time_invariant(item):
+            # one fetch per DISTINCT source image of the range (a looping sequence shows the same few frames
+            # over and over): the layer's batch keys say which frames share one
+            keys = item.layer.get_keys(layer_times[idx])
+            fetched: dict = {}
+            for j, f in enumerate(idx):
+                k = keys[j]
+                if k not in fetched:
+                    fetched[k] = item.fg_image_device(float(times[f]), comp.cache)
+                images[j] = fetched[k]
         else:
             for j, f in enumerate(idx):
                 images[j] = item.fg_image_device(float(times[f]), comp.cache)

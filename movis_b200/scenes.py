@@ -239,6 +239,15 @@ class LoopedLayer:
     def get_key(self, time: float):
         return self.layer.get_key(self._local(time)) if 0 <= time < self.duration else None
 
+    def get_keys(self, times):
+        """Optional batch form of ``get_key`` (this package's range planner uses it when a layer has one)."""
+        times = np.asarray(times, dtype=np.float64)
+        if not hasattr(self.layer, "get_keys"):
+            return np.array([self.get_key(float(t)) for t in times], dtype=object)
+        keys = np.asarray(self.layer.get_keys(times % self.layer.duration), dtype=object)
+        keys[(times < 0) | (times >= self.duration)] = None
+        return keys
+
     def __call__(self, time: float):
         return self.layer(self._local(time)) if 0 <= time < self.duration else None
 
