@@ -56,6 +56,27 @@ def test_cost_balanced_shard_range():
     assert c.shape == (150,) and c[-1] > c[0] > 0              # the layers grow over the timeline
 
 
+def test_range_plan_slices_and_batch_keys_need_no_gpu():
+    """Host-only pieces of the range renderer: RangePlan.slice (what stream_frames launches per copy
+    batch) and the batch key lookups (TimelineMixin.get_states / ImageSequence.get_keys, scenes.LoopedLayer)."""
+    import movis_b200 as mv
+    from movis_b200 import _native, scenes
+    from movis_b200.render import RangePlan
+    desc = np.zeros(10, dtype=_native.LAYER_DTYPE)
+    desc["bbox_x"] = np.arange(10)
+    plan = RangePlan(desc, np.array([0, 3, 3, 7, 10], dtype=np.int32), [])
+    part = plan.slice(1, 3)
+    assert part.n_frames == 2 and part.offsets.tolist() == [0, 0, 4] and part.descriptors["bbox_x"].tolist() == [3, 4, 5, 6]
+    assert plan.slice(0, 4).offsets.tolist() == plan.offsets.tolist() and plan.slice(3, 4).descriptors["bbox_x"].tolist() == [7, 8, 9]
+    frames = [np.full((2, 2, 4), i, np.uint8) for i in range(4)]
+    seq = mv.layer.ImageSequence.from_files(frames, each_duration=0.25)
+    ts = np.array([-0.1, 0.0, 0.24, 0.25, 0.6, 0.99, 1.0, 3.0])
+    assert seq.get_keys(ts).tolist() == [seq.get_key(float(t)) for t in ts] == [-1, 0, 0, 1, 2, 3, -1, -1]
+    loop = scenes.LoopedLayer(seq, 2.0)
+    ts = np.array([-0.5, 0.0, 0.3, 1.0, 1.26, 1.99, 2.0])
+    assert loop.get_keys(ts).tolist() == [loop.get_key(float(t)) for t in ts] == [None, 0, 1, 0, 1, 3, None]
+
+
 def _free_port() -> int:
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
